@@ -1,0 +1,317 @@
+// zkm_field.cuh -- Montgomery prime fields on 32-bit limbs and the quadratic
+// extension Fq2 = Fq[u]/(u^2+1) used by G2 of both BLS12-381 and BN254.
+//
+// Semantics replaced (un-vendored ark-ff 0.3.0, pinned at
+// /root/reference/Cargo.lock:229-230): Fp256/Fp384 mul_assign / square_in_place /
+// add_assign / sub_assign / neg (src/fields/macros.rs, arithmetic.rs) and
+// QuadExtField (src/fields/models/quadratic_extension.rs).  Values are value*R mod p
+// with R = 2^(32*N) = 2^(64*limbs64): the byte image of an element is identical to
+// ark-ff's little-endian u64-limb storage, and every operation returns the fully
+// reduced representative, so results are bit-identical to ark-ff's.
+//
+// The Montgomery product is an operand-scanning CIOS on ABSOLUTE columns with two
+// accumulators: acc[0] takes every carry chain that starts on an even column,
+// acc[1] every chain that starts on an odd column.  A chain is lo(a_i*b_j) into
+// column k, hi(a_i*b_j) into column k+1, for i stepping by two -- i.e. exactly the
+// mad.lo.cc / madc.hi.cc pairing that ptxas turns into one IMAD.WIDE.U32.X on an
+// aligned register pair.  Column j of the two accumulators is merged right before
+// the reduction factor m_j is formed; the carry of a chain lands in a column no
+// chain body has reached yet, so it can never overflow.  Requires a spare top bit
+// in the modulus (381/384, 255/256, 254/256 here).
+#pragma once
+#include "zkm_arith.cuh"
+#include "zkm_constants.cuh"
+
+namespace zkm {
+
+// ----------------------------------------------------------------------------- parameter tags
+#define ZKM_DEFINE_FP_PARAMS(Tag, PREFIX, NLIMBS)                                   \
+    struct Tag {                                                                    \
+        static constexpr int N = NLIMBS;                                            \
+        static constexpr uint32_t INV = PREFIX##_INV32;                             \
+        static constexpr int BITS = PREFIX##_BITS;                                  \
+        static ZKM_DEV uint32_t mod(int i) { return PREFIX##_MOD[i]; }              \
+        static ZKM_DEV uint32_t one(int i) { return PREFIX##_ONE[i]; }              \
+        static ZKM_DEV uint32_t r2(int i) { return PREFIX##_R2[i]; }                \
+    };
+
+ZKM_DEFINE_FP_PARAMS(Bls12_381_FqP, BLS12_381_FQ, 12)
+ZKM_DEFINE_FP_PARAMS(Bls12_381_FrP, BLS12_381_FR, 8)
+ZKM_DEFINE_FP_PARAMS(Bn254_FqP, BN254_FQ, 8)
+ZKM_DEFINE_FP_PARAMS(Bn254_FrP, BN254_FR, 8)
+
+// ----------------------------------------------------------------------------- Fp
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    typedef P Params;
+    uint32_t l[N];
+
+    static ZKM_DEV Fp zero() {
+        Fp r;
+        ZKM_UNROLL
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    static ZKM_DEV Fp one() {
+        Fp r;
+        ZKM_UNROLL
+        for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    static ZKM_DEV Fp r2() {
+        Fp r;
+        ZKM_UNROLL
+        for (int i = 0; i < N; i++) r.l[i] = P::r2(i);
+        return r;
+    }
+    ZKM_DEV bool is_zero() const {
+        uint32_t o = 0;
+        ZKM_UNROLL
+        for (int i = 0; i < N; i++) o |= l[i];
+        return o == 0;
+    }
+    ZKM_DEV bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+        ZKM_UNROLL
+        for (int i = 0; i < N; i++) o |= (l[i] ^ b.l[i]);
+        return o == 0;
+    }
+    ZKM_DEV bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = (t >= p) ? t - p : t      (t < 2p)
+template <class P>
+ZKM_DEV void fp_final_sub(Fp<P>& t) {
+    constexpr int N = P::N;
+    uint32_t d[N];
+    d[0] = ptx::sub_cc(t.l[0], P::mod(0));
+    ZKM_UNROLL
+    for (int i = 1; i < N; i++) d[i] = ptx::subc_cc(t.l[i], P::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);  // 0xffffffff when t < p
+    ZKM_UNROLL
+    for (int i = 0; i < N; i++) t.l[i] = borrow ? t.l[i] : d[i];
+}
+
+template <class P>
+ZKM_DEV Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+    ZKM_UNROLL
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    r.l[N - 1] = ptx::addc(a.l[N - 1], b.l[N - 1]);
+    fp_final_sub(r);
+    return r;
+}
+
+template <class P>
+ZKM_DEV Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+    ZKM_UNROLL
+    for (int i = 1; i < N; i++) r.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+    uint32_t mask = ptx::subc(0, 0);  // all ones when a < b
+    r.l[0] = ptx::add_cc(r.l[0], P::mod(0) & mask);
+    ZKM_UNROLL
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], P::mod(i) & mask);
+    r.l[N - 1] = ptx::addc(r.l[N - 1], P::mod(N - 1) & mask);
+    return r;
+}
+
+template <class P>
+ZKM_DEV Fp<P> fp_neg(const Fp<P>& a) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    uint32_t nz = 0;
+    ZKM_UNROLL
+    for (int i = 0; i < N; i++) nz |= a.l[i];
+    uint32_t mask = nz ? 0xffffffffu : 0u;  // -0 = 0
+    r.l[0] = ptx::sub_cc(P::mod(0) & mask, a.l[0]);
+    ZKM_UNROLL
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::subc_cc(P::mod(i) & mask, a.l[i]);
+    r.l[N - 1] = ptx::subc(P::mod(N - 1) & mask, a.l[N - 1]);
+    return r;
+}
+
+template <class P>
+ZKM_DEV Fp<P> fp_dbl(const Fp<P>& a) {
+    return fp_add(a, a);
+}
+
+// Montgomery product a*b*R^-1 mod p, fully reduced.
+template <class P>
+ZKM_DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    static_assert((N & 1) == 0, "even limb count required");
+    uint32_t acc[2][2 * N + 2];
+    ZKM_UNROLL
+    for (int i = 0; i < 2 * N + 2; i++) {
+        acc[0][i] = 0;
+        acc[1][i] = 0;
+    }
+    ZKM_UNROLL
+    for (int j = 0; j < N; j++) {
+        uint32_t* X = acc[j & 1];        // chain of even a-limbs starts at column j
+        uint32_t* Y = acc[(j & 1) ^ 1];  // chain of odd a-limbs starts at column j+1
+        const uint32_t bj = b.l[j];
+        if (j == 0) {
+            ZKM_UNROLL
+            for (int i = 1; i < N; i += 2) {
+                Y[i] = ptx::mul_lo(a.l[i], bj);
+                Y[i + 1] = ptx::mul_hi(a.l[i], bj);
+            }
+            ZKM_UNROLL
+            for (int i = 0; i < N; i += 2) {
+                X[i] = ptx::mul_lo(a.l[i], bj);
+                X[i + 1] = ptx::mul_hi(a.l[i], bj);
+            }
+        } else {
+            // merge column j of the two accumulators; its carry enters the Y chain
+            X[j] = ptx::add_cc(X[j], Y[j]);
+            ZKM_UNROLL
+            for (int i = 1; i < N; i += 2) {
+                Y[j + i] = ptx::madc_lo_cc(a.l[i], bj, Y[j + i]);
+                Y[j + i + 1] = ptx::madc_hi_cc(a.l[i], bj, Y[j + i + 1]);
+            }
+            Y[j + N + 1] = ptx::addc(Y[j + N + 1], 0);
+            X[j] = ptx::mad_lo_cc(a.l[0], bj, X[j]);
+            X[j + 1] = ptx::madc_hi_cc(a.l[0], bj, X[j + 1]);
+            ZKM_UNROLL
+            for (int i = 2; i < N; i += 2) {
+                X[j + i] = ptx::madc_lo_cc(a.l[i], bj, X[j + i]);
+                X[j + i + 1] = ptx::madc_hi_cc(a.l[i], bj, X[j + i + 1]);
+            }
+            X[j + N] = ptx::addc(X[j + N], 0);
+        }
+        const uint32_t m = ptx::mul_lo(X[j], P::INV);
+        Y[j + 1] = ptx::mad_lo_cc(m, P::mod(1), Y[j + 1]);
+        Y[j + 2] = ptx::madc_hi_cc(m, P::mod(1), Y[j + 2]);
+        ZKM_UNROLL
+        for (int i = 3; i < N; i += 2) {
+            Y[j + i] = ptx::madc_lo_cc(m, P::mod(i), Y[j + i]);
+            Y[j + i + 1] = ptx::madc_hi_cc(m, P::mod(i), Y[j + i + 1]);
+        }
+        Y[j + N + 1] = ptx::addc(Y[j + N + 1], 0);
+        X[j] = ptx::mad_lo_cc(m, P::mod(0), X[j]);
+        X[j + 1] = ptx::madc_hi_cc(m, P::mod(0), X[j + 1]);
+        ZKM_UNROLL
+        for (int i = 2; i < N; i += 2) {
+            X[j + i] = ptx::madc_lo_cc(m, P::mod(i), X[j + i]);
+            X[j + i + 1] = ptx::madc_hi_cc(m, P::mod(i), X[j + i + 1]);
+        }
+        X[j + N] = ptx::addc(X[j + N], 0);
+    }
+    Fp<P> r;
+    r.l[0] = ptx::add_cc(acc[0][N], acc[1][N]);
+    ZKM_UNROLL
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(acc[0][N + i], acc[1][N + i]);
+    r.l[N - 1] = ptx::addc(acc[0][2 * N - 1], acc[1][2 * N - 1]);
+    fp_final_sub(r);
+    return r;
+}
+
+template <class P>
+ZKM_DEV Fp<P> fp_sqr(const Fp<P>& a) {
+    return fp_mul(a, a);
+}
+
+// a^e for a little-endian multi-limb exponent (setup / normalisation only).
+template <class P>
+ZKM_DEV Fp<P> fp_pow_limbs(const Fp<P>& a, const uint32_t* e, int nlimbs) {
+    Fp<P> r = Fp<P>::one();
+    bool started = false;
+    for (int i = nlimbs - 1; i >= 0; i--) {
+        for (int b = 31; b >= 0; b--) {
+            if (started) r = fp_sqr(r);
+            if ((e[i] >> b) & 1) {
+                r = started ? fp_mul(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+
+template <class P>
+ZKM_DEV Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
+    uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+    return fp_pow_limbs(a, w, 2);
+}
+
+// Fermat inverse a^(p-2); a != 0.
+template <class P>
+ZKM_DEV Fp<P> fp_inv(const Fp<P>& a) {
+    constexpr int N = P::N;
+    uint32_t e[N];
+    uint32_t borrow = 2;
+    for (int i = 0; i < N; i++) {
+        uint32_t m = P::mod(i);
+        e[i] = m - borrow;
+        borrow = (m < borrow) ? 1u : 0u;
+    }
+    return fp_pow_limbs(a, e, N);
+}
+
+template <class P> ZKM_DEV Fp<P> operator+(const Fp<P>& a, const Fp<P>& b) { return fp_add(a, b); }
+template <class P> ZKM_DEV Fp<P> operator-(const Fp<P>& a, const Fp<P>& b) { return fp_sub(a, b); }
+template <class P> ZKM_DEV Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
+template <class P> ZKM_DEV Fp<P> sqr(const Fp<P>& a) { return fp_sqr(a); }
+template <class P> ZKM_DEV Fp<P> dbl(const Fp<P>& a) { return fp_dbl(a); }
+template <class P> ZKM_DEV Fp<P> neg(const Fp<P>& a) { return fp_neg(a); }
+template <class P> ZKM_DEV Fp<P> inv(const Fp<P>& a) { return fp_inv(a); }
+
+// ----------------------------------------------------------------------------- Fp2 = Fp[u]/(u^2+1)
+template <class P>
+struct Fp2 {
+    typedef P Params;
+    Fp<P> c0, c1;
+    static ZKM_DEV Fp2 zero() { Fp2 r; r.c0 = Fp<P>::zero(); r.c1 = Fp<P>::zero(); return r; }
+    static ZKM_DEV Fp2 one() { Fp2 r; r.c0 = Fp<P>::one(); r.c1 = Fp<P>::zero(); return r; }
+    ZKM_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    ZKM_DEV bool operator==(const Fp2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    ZKM_DEV bool operator!=(const Fp2& b) const { return !(*this == b); }
+};
+
+template <class P> ZKM_DEV Fp2<P> operator+(const Fp2<P>& a, const Fp2<P>& b) { Fp2<P> r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+template <class P> ZKM_DEV Fp2<P> operator-(const Fp2<P>& a, const Fp2<P>& b) { Fp2<P> r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+template <class P> ZKM_DEV Fp2<P> neg(const Fp2<P>& a) { Fp2<P> r; r.c0 = neg(a.c0); r.c1 = neg(a.c1); return r; }
+template <class P> ZKM_DEV Fp2<P> dbl(const Fp2<P>& a) { Fp2<P> r; r.c0 = dbl(a.c0); r.c1 = dbl(a.c1); return r; }
+// Karatsuba: (a0 b0 - a1 b1) + ((a0+a1)(b0+b1) - a0 b0 - a1 b1) u
+template <class P>
+ZKM_DEV Fp2<P> operator*(const Fp2<P>& a, const Fp2<P>& b) {
+    Fp<P> v0 = a.c0 * b.c0;
+    Fp<P> v1 = a.c1 * b.c1;
+    Fp<P> s = (a.c0 + a.c1) * (b.c0 + b.c1);
+    Fp2<P> r;
+    r.c0 = v0 - v1;
+    r.c1 = (s - v0) - v1;
+    return r;
+}
+// (a0+a1)(a0-a1) + 2 a0 a1 u
+template <class P>
+ZKM_DEV Fp2<P> sqr(const Fp2<P>& a) {
+    Fp<P> t = a.c0 * a.c1;
+    Fp2<P> r;
+    r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
+    r.c1 = dbl(t);
+    return r;
+}
+template <class P>
+ZKM_DEV Fp2<P> inv(const Fp2<P>& a) {
+    Fp<P> n = inv(sqr(a.c0) + sqr(a.c1));
+    Fp2<P> r;
+    r.c0 = a.c0 * n;
+    r.c1 = neg(a.c1 * n);
+    return r;
+}
+
+typedef Fp<Bls12_381_FqP> Bls12_381_Fq;
+typedef Fp<Bls12_381_FrP> Bls12_381_Fr;
+typedef Fp<Bn254_FqP> Bn254_Fq;
+typedef Fp<Bn254_FrP> Bn254_Fr;
+typedef Fp2<Bls12_381_FqP> Bls12_381_Fq2;
+typedef Fp2<Bn254_FqP> Bn254_Fq2;
+
+}  // namespace zkm
