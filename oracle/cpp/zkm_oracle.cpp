@@ -1,0 +1,639 @@
+// TEST INFRASTRUCTURE ONLY (oracle) -- never linked, loaded or called by the product path.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+//
+// CPU restatement, in C++17 on 64-bit limbs, of the arkworks 0.3.0 algorithms that sit on
+// zkMember's hot path.  The arkworks crates are NOT vendored under /root/reference (they are
+// crates.io dependencies pinned in /root/reference/Cargo.lock: ark-ec 0.3.0 :179-180, ark-poly
+// 0.3.0 :338-339, ark-ff 0.3.0 :229-230) and there is no Rust toolchain in this image, so the
+// published algorithms are restated here from SURVEY.md Appendix A; the reference reaches them
+// from /root/reference/benches/groth16.rs:115 (Groth16::prove) and benches/marlin.rs:202,311.
+//
+// PARITY UNPINNED against the arkworks binaries: the reference holds no golden vector or
+// known-answer test for MSM / FFT.  What pins this file instead:
+//   * tests/test_oracle_cpp.py checks every function against oracle/py/exact.py (exact big-int
+//     arithmetic, algorithm-independent definitions) and against published constants;
+//   * results are mathematically unique (normalised affine point; field elements), so any correct
+//     implementation of the published algorithm produces these bytes.
+//
+// Restated functions (crate-relative upstream paths):
+//   Fp<P>::mul/add/sub/...       ark-ff  src/fields/macros.rs, arithmetic.rs  (Montgomery CIOS, R = 2^(64 n))
+//   Fp2                          ark-ff  src/fields/models/quadratic_extension.rs (Karatsuba, u^2 = -1)
+//   Jac::add_mixed/add/dbl/...   ark-ec  src/models/short_weierstrass_jacobian.rs
+//                                (madd-2007-bl, add-2007-bl, dbl-2009-l, into_affine)
+//   msm_arkworks                 ark-ec  src/msm/variable_base.rs  VariableBaseMSM::multi_scalar_mul
+//   ln_without_floats            ark-ec  src/msm/mod.rs
+//   io_helper / oi_helper / derange / fft / ifft / coset_*   ark-poly src/domain/radix2/fft.rs, mod.rs,
+//                                                            src/domain/mod.rs (distribute_powers)
+// Parallelism mirrors rayon's use upstream: one task per MSM window, butterflies split across threads.
+#include <omp.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+typedef uint64_t u64;
+typedef unsigned __int128 u128;
+
+// ----------------------------------------------------------------------------- field parameters
+template <int N_>
+struct FieldConsts {
+    static constexpr int N = N_;
+    u64 p[N_];
+    u64 one[N_];  // R mod p
+    u64 r2[N_];   // R^2 mod p
+    u64 inv;      // -p^-1 mod 2^64
+    int bits;
+};
+
+template <int N>
+static bool geq(const u64* a, const u64* b) {
+    for (int i = N - 1; i >= 0; i--) {
+        if (a[i] != b[i]) return a[i] > b[i];
+    }
+    return true;
+}
+template <int N>
+static u64 sub_n(u64* r, const u64* a, const u64* b) {
+    u64 borrow = 0;
+    for (int i = 0; i < N; i++) {
+        u128 t = (u128)a[i] - b[i] - borrow;
+        r[i] = (u64)t;
+        borrow = (u64)(t >> 64) & 1;
+    }
+    return borrow;
+}
+template <int N>
+static u64 add_n(u64* r, const u64* a, const u64* b) {
+    u64 carry = 0;
+    for (int i = 0; i < N; i++) {
+        u128 t = (u128)a[i] + b[i] + carry;
+        r[i] = (u64)t;
+        carry = (u64)(t >> 64);
+    }
+    return carry;
+}
+
+// derive R, R^2, inv from the modulus alone (no generated tables in the oracle)
+template <int N>
+static FieldConsts<N> make_consts(const u64* p) {
+    FieldConsts<N> c;
+    memcpy(c.p, p, sizeof(c.p));
+    int bits = 64 * N;
+    while (bits > 0 && !((p[(bits - 1) / 64] >> ((bits - 1) % 64)) & 1)) bits--;
+    c.bits = bits;
+    u64 x = 1;  // Newton: x = p^-1 mod 2^64
+    for (int i = 0; i < 6; i++) x *= 2 - p[0] * x;
+    c.inv = (u64)0 - x;
+    // t = 1; double it 64N times (-> R mod p) and 128N times (-> R^2 mod p)
+    u64 t[N];
+    memset(t, 0, sizeof(t));
+    t[0] = 1;
+    for (int k = 0; k < 128 * N; k++) {
+        u64 carry = add_n<N>(t, t, t);
+        if (carry || geq<N>(t, p)) sub_n<N>(t, t, p);
+        if (k == 64 * N - 1) memcpy(c.one, t, sizeof(t));
+    }
+    memcpy(c.r2, t, sizeof(t));
+    return c;
+}
+
+static const u64 BLS_FQ_P[6] = {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL,
+                                0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL};
+static const u64 BLS_FR_P[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL,
+                                0x73eda753299d7d48ULL};
+static const u64 BN_FQ_P[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL,
+                               0x30644e72e131a029ULL};
+static const u64 BN_FR_P[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL,
+                               0x30644e72e131a029ULL};
+
+struct BlsFqTag { static constexpr int N = 6; static const FieldConsts<6> C; };
+struct BlsFrTag { static constexpr int N = 4; static const FieldConsts<4> C; };
+struct BnFqTag  { static constexpr int N = 4; static const FieldConsts<4> C; };
+struct BnFrTag  { static constexpr int N = 4; static const FieldConsts<4> C; };
+const FieldConsts<6> BlsFqTag::C = make_consts<6>(BLS_FQ_P);
+const FieldConsts<4> BlsFrTag::C = make_consts<4>(BLS_FR_P);
+const FieldConsts<4> BnFqTag::C = make_consts<4>(BN_FQ_P);
+const FieldConsts<4> BnFrTag::C = make_consts<4>(BN_FR_P);
+
+// ----------------------------------------------------------------------------- Fp (Montgomery)
+template <class T>
+struct Fp {
+    static constexpr int N = T::N;
+    static constexpr int WORDS = T::N;
+    u64 l[N];
+
+    static Fp zero() { Fp r; memset(r.l, 0, sizeof(r.l)); return r; }
+    static Fp one() { Fp r; memcpy(r.l, T::C.one, sizeof(r.l)); return r; }
+    static Fp from_u64(u64 v) {  // canonical small integer -> Montgomery
+        Fp t = zero();
+        t.l[0] = v;
+        Fp r2;
+        memcpy(r2.l, T::C.r2, sizeof(r2.l));
+        return t * r2;
+    }
+    bool is_zero() const { u64 o = 0; for (int i = 0; i < N; i++) o |= l[i]; return o == 0; }
+    bool operator==(const Fp& b) const { return memcmp(l, b.l, sizeof(l)) == 0; }
+    bool operator!=(const Fp& b) const { return !(*this == b); }
+
+    Fp operator+(const Fp& b) const {
+        Fp r;
+        u64 carry = add_n<N>(r.l, l, b.l);
+        if (carry || geq<N>(r.l, T::C.p)) sub_n<N>(r.l, r.l, T::C.p);
+        return r;
+    }
+    Fp operator-(const Fp& b) const {
+        Fp r;
+        if (sub_n<N>(r.l, l, b.l)) add_n<N>(r.l, r.l, T::C.p);
+        return r;
+    }
+    Fp neg() const {
+        if (is_zero()) return *this;
+        Fp r;
+        sub_n<N>(r.l, T::C.p, l);
+        return r;
+    }
+    Fp dbl() const { return *this + *this; }
+    // CIOS Montgomery product (ark-ff macros.rs impl_field_mul_assign), fully reduced
+    Fp operator*(const Fp& b) const {
+        u64 t[N + 2];
+        memset(t, 0, sizeof(t));
+        const u64* p = T::C.p;
+        for (int i = 0; i < N; i++) {
+            u64 carry = 0;
+            for (int j = 0; j < N; j++) {
+                u128 s = (u128)l[j] * b.l[i] + t[j] + carry;
+                t[j] = (u64)s;
+                carry = (u64)(s >> 64);
+            }
+            u128 s = (u128)t[N] + carry;
+            t[N] = (u64)s;
+            t[N + 1] = (u64)(s >> 64);
+            u64 m = t[0] * T::C.inv;
+            s = (u128)m * p[0] + t[0];
+            carry = (u64)(s >> 64);
+            for (int j = 1; j < N; j++) {
+                s = (u128)m * p[j] + t[j] + carry;
+                t[j - 1] = (u64)s;
+                carry = (u64)(s >> 64);
+            }
+            s = (u128)t[N] + carry;
+            t[N - 1] = (u64)s;
+            t[N] = t[N + 1] + (u64)(s >> 64);
+        }
+        Fp r;
+        if (t[N] || geq<N>(t, p)) sub_n<N>(r.l, t, p);
+        else memcpy(r.l, t, sizeof(r.l));
+        return r;
+    }
+    Fp sqr() const { return *this * *this; }
+    Fp pow_limbs(const u64* e, int n) const {
+        Fp r = one();
+        bool started = false;
+        for (int i = n - 1; i >= 0; i--)
+            for (int b = 63; b >= 0; b--) {
+                if (started) r = r.sqr();
+                if ((e[i] >> b) & 1) { r = started ? r * *this : *this; started = true; }
+            }
+        return r;
+    }
+    Fp inverse() const {  // a^(p-2); value-identical to ark-ff's binary-EGCD inverse
+        u64 e[N], two[N];
+        memset(two, 0, sizeof(two));
+        two[0] = 2;
+        sub_n<N>(e, T::C.p, two);
+        return pow_limbs(e, N);
+    }
+    void into_repr(u64* out) const {  // Montgomery -> canonical integer
+        Fp o = zero();
+        o.l[0] = 1;
+        Fp r = *this * o;
+        memcpy(out, r.l, sizeof(r.l));
+    }
+};
+
+// ----------------------------------------------------------------------------- Fp2 = Fp[u]/(u^2+1)
+template <class T>
+struct Fp2 {
+    static constexpr int WORDS = 2 * T::N;
+    Fp<T> c0, c1;
+    static Fp2 zero() { return {Fp<T>::zero(), Fp<T>::zero()}; }
+    static Fp2 one() { return {Fp<T>::one(), Fp<T>::zero()}; }
+    bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    bool operator==(const Fp2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    bool operator!=(const Fp2& b) const { return !(*this == b); }
+    Fp2 operator+(const Fp2& b) const { return {c0 + b.c0, c1 + b.c1}; }
+    Fp2 operator-(const Fp2& b) const { return {c0 - b.c0, c1 - b.c1}; }
+    Fp2 neg() const { return {c0.neg(), c1.neg()}; }
+    Fp2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+    Fp2 operator*(const Fp2& b) const {  // Karatsuba, non-residue -1
+        Fp<T> v0 = c0 * b.c0, v1 = c1 * b.c1;
+        Fp<T> s = (c0 + c1) * (b.c0 + b.c1);
+        return {v0 - v1, s - v0 - v1};
+    }
+    Fp2 sqr() const { return *this * *this; }
+    Fp2 inverse() const {
+        Fp<T> n = (c0.sqr() + c1.sqr()).inverse();
+        return {c0 * n, (c1 * n).neg()};
+    }
+};
+
+// ----------------------------------------------------------------------------- Jacobian group (a = 0)
+template <class F>
+struct Aff {
+    F x, y;
+    bool inf;
+};
+
+template <class F>
+struct Jac {
+    F x, y, z;
+    static Jac zero() { return {F::zero(), F::one(), F::zero()}; }
+    bool is_zero() const { return z.is_zero(); }
+
+    // dbl-2009-l
+    void double_in_place() {
+        if (is_zero()) return;
+        F a = x.sqr();
+        F b = y.sqr();
+        F c = b.sqr();
+        F d = ((x + b).sqr() - a - c).dbl();
+        F e = a + a.dbl();
+        F f = e.sqr();
+        z = (z * y).dbl();
+        x = f - d - d;
+        y = (d - x) * e - c.dbl().dbl().dbl();
+    }
+    // madd-2007-bl
+    void add_assign_mixed(const Aff<F>& o) {
+        if (o.inf) return;
+        if (is_zero()) { x = o.x; y = o.y; z = F::one(); return; }
+        F z1z1 = z.sqr();
+        F u2 = o.x * z1z1;
+        F s2 = (o.y * z) * z1z1;
+        if (x == u2 && y == s2) { double_in_place(); return; }
+        F h = u2 - x;
+        F hh = h.sqr();
+        F i = hh.dbl().dbl();
+        F j = h * i;
+        F r = (s2 - y).dbl();
+        F v = x * i;
+        F x3 = r.sqr() - j - v.dbl();
+        F y3 = r * (v - x3) - (y * j).dbl();
+        z = (z + h).sqr() - z1z1 - hh;
+        x = x3;
+        y = y3;
+    }
+    // add-2007-bl
+    void add_assign(const Jac& o) {
+        if (is_zero()) { *this = o; return; }
+        if (o.is_zero()) return;
+        F z1z1 = z.sqr();
+        F z2z2 = o.z.sqr();
+        F u1 = x * z2z2;
+        F u2 = o.x * z1z1;
+        F s1 = y * o.z * z2z2;
+        F s2 = o.y * z * z1z1;
+        if (u1 == u2 && s1 == s2) { double_in_place(); return; }
+        F h = u2 - u1;
+        F i = h.dbl().sqr();
+        F j = h * i;
+        F r = (s2 - s1).dbl();
+        F v = u1 * i;
+        F x3 = r.sqr() - j - v.dbl();
+        F y3 = r * (v - x3) - (s1 * j).dbl();
+        z = ((z + o.z).sqr() - z1z1 - z2z2) * h;
+        x = x3;
+        y = y3;
+    }
+    Aff<F> into_affine() const {
+        if (is_zero()) return {F::zero(), F::one(), true};
+        F zi = z.inverse();
+        F zi2 = zi.sqr();
+        return {x * zi2, y * zi2 * zi, false};
+    }
+};
+
+// ----------------------------------------------------------------------------- MSM (ark-ec 0.3.0)
+static inline int ceil_log2(size_t a) {  // ark_std::log2
+    if (a <= 1) return 0;
+    int l = 0;
+    size_t v = a - 1;
+    while (v) { l++; v >>= 1; }
+    return l;
+}
+static inline size_t ln_without_floats(size_t a) { return (size_t)ceil_log2(a) * 69 / 100; }
+
+static inline bool scalar_is_zero(const u64* s) { return (s[0] | s[1] | s[2] | s[3]) == 0; }
+static inline bool scalar_is_one(const u64* s) { return s[0] == 1 && (s[1] | s[2] | s[3]) == 0; }
+// (s >> shift) mod 2^c, c <= 31
+static inline u64 scalar_window(const u64* s, int shift, int c) {
+    int limb = shift / 64, off = shift % 64;
+    u64 v = s[limb] >> off;
+    if (off && limb + 1 < 4) v |= s[limb + 1] << (64 - off);
+    return v & ((1ULL << c) - 1);
+}
+
+template <class F>
+static Aff<F> msm_arkworks(const Aff<F>* bases, const u64* scalars, size_t size, int num_bits, int threads) {
+    int c = size < 32 ? 3 : (int)ln_without_floats(size) + 2;
+    std::vector<int> window_starts;
+    for (int w = 0; w < num_bits; w += c) window_starts.push_back(w);
+    std::vector<Jac<F>> window_sums(window_starts.size());
+    int nt = threads > 0 ? threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (size_t wi = 0; wi < window_starts.size(); wi++) {
+        int w_start = window_starts[wi];
+        Jac<F> res = Jac<F>::zero();
+        std::vector<Jac<F>> buckets(((size_t)1 << c) - 1, Jac<F>::zero());
+        for (size_t i = 0; i < size; i++) {
+            const u64* s = scalars + 4 * i;
+            if (scalar_is_zero(s)) continue;
+            if (scalar_is_one(s)) {
+                if (w_start == 0) res.add_assign_mixed(bases[i]);
+            } else {
+                u64 d = scalar_window(s, w_start, c);
+                if (d != 0) buckets[d - 1].add_assign_mixed(bases[i]);
+            }
+        }
+        Jac<F> running = Jac<F>::zero();
+        for (size_t b = buckets.size(); b-- > 0;) {
+            running.add_assign(buckets[b]);
+            res.add_assign(running);
+        }
+        window_sums[wi] = res;
+    }
+    Jac<F> total = Jac<F>::zero();
+    for (size_t wi = window_sums.size(); wi-- > 1;) {
+        total.add_assign(window_sums[wi]);
+        for (int k = 0; k < c; k++) total.double_in_place();
+    }
+    total.add_assign(window_sums[0]);
+    return total.into_affine();
+}
+
+// ----------------------------------------------------------------------------- NTT (ark-poly 0.3.0)
+template <class F>
+struct Domain {
+    int log_n;
+    size_t n;
+    F group_gen, group_gen_inv, size_inv, generator, generator_inv;
+};
+
+template <class T>
+static bool make_domain(Domain<Fp<T>>& d, int log_n, u64 generator, int two_adicity) {
+    typedef Fp<T> F;
+    if (log_n > two_adicity) return false;
+    d.log_n = log_n;
+    d.n = (size_t)1 << log_n;
+    // TWO_ADIC_ROOT = g^((p-1)/2^s)
+    u64 e[T::N], onev[T::N];
+    memset(onev, 0, sizeof(onev));
+    onev[0] = 1;
+    sub_n<T::N>(e, T::C.p, onev);
+    for (int k = 0; k < two_adicity; k++) {  // e >>= 1
+        for (int i = 0; i < T::N; i++) e[i] = (e[i] >> 1) | (i + 1 < T::N ? e[i + 1] << 63 : 0);
+    }
+    F g = F::from_u64(generator);
+    F root = g.pow_limbs(e, T::N);
+    for (int k = log_n; k < two_adicity; k++) root = root.sqr();
+    d.group_gen = root;
+    d.group_gen_inv = root.inverse();
+    d.size_inv = F::from_u64((u64)d.n).inverse();
+    d.generator = g;
+    d.generator_inv = g.inverse();
+    return true;
+}
+
+static inline size_t bitrev(size_t a, int bits) {
+    size_t r = 0;
+    for (int i = 0; i < bits; i++) { r = (r << 1) | (a & 1); a >>= 1; }
+    return r;
+}
+
+template <class F>
+static void derange(F* x, int log_n) {
+    size_t n = (size_t)1 << log_n;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        size_t r = bitrev(i, log_n);
+        if (i < r) std::swap(x[i], x[r]);
+    }
+}
+
+template <class F>
+static std::vector<F> roots_of_unity(const F& root, size_t n_half) {  // [root^0 .. root^(n/2-1)]
+    std::vector<F> r(n_half ? n_half : 1);
+    int nt = omp_get_max_threads();
+    size_t chunk = (n_half + nt - 1) / (nt ? nt : 1);
+    if (chunk == 0) chunk = 1;
+#pragma omp parallel for schedule(static, 1)
+    for (size_t start = 0; start < n_half; start += chunk) {
+        u64 e[1] = {(u64)start};
+        F cur = root.pow_limbs(e, 1);
+        size_t end = std::min(n_half, start + chunk);
+        for (size_t i = start; i < end; i++) { r[i] = cur; cur = cur * root; }
+    }
+    return r;
+}
+
+// in-order input, bit-reversed output (DIF)
+template <class F>
+static void io_helper(F* x, int log_n, const F& root) {
+    size_t n = (size_t)1 << log_n;
+    std::vector<F> roots = roots_of_unity(root, n / 2);
+    for (size_t gap = n / 2; gap > 0; gap /= 2) {
+        size_t step = n / (2 * gap);  // == num_chunks
+#pragma omp parallel for schedule(static)
+        for (size_t idx = 0; idx < n / 2; idx++) {
+            size_t chunk = idx / gap, j = idx % gap;
+            F* lo = x + chunk * 2 * gap + j;
+            F* hi = lo + gap;
+            F neg = *lo - *hi;
+            *lo = *lo + *hi;
+            *hi = neg * roots[j * step];
+        }
+    }
+}
+// bit-reversed input, in-order output (DIT)
+template <class F>
+static void oi_helper(F* x, int log_n, const F& root) {
+    size_t n = (size_t)1 << log_n;
+    std::vector<F> roots = roots_of_unity(root, n / 2);
+    for (size_t gap = 1; gap < n; gap *= 2) {
+        size_t step = n / (2 * gap);
+#pragma omp parallel for schedule(static)
+        for (size_t idx = 0; idx < n / 2; idx++) {
+            size_t chunk = idx / gap, j = idx % gap;
+            F* lo = x + chunk * 2 * gap + j;
+            F* hi = lo + gap;
+            *hi = *hi * roots[j * step];
+            F neg = *lo - *hi;
+            *lo = *lo + *hi;
+            *hi = neg;
+        }
+    }
+}
+template <class F>
+static void distribute_powers_and_mul_by_const(F* x, size_t n, const F& g, const F& c) {
+    F pow = c;
+    for (size_t i = 0; i < n; i++) { x[i] = x[i] * pow; pow = pow * g; }
+}
+
+template <class F>
+static void ntt_arkworks(F* x, const Domain<F>& d, int inverse, int coset) {
+    if (!inverse) {
+        if (coset) distribute_powers_and_mul_by_const(x, d.n, d.generator, F::one());
+        io_helper(x, d.log_n, d.group_gen);
+        derange(x, d.log_n);
+    } else {
+        derange(x, d.log_n);
+        oi_helper(x, d.log_n, d.group_gen_inv);
+        if (coset) {
+            distribute_powers_and_mul_by_const(x, d.n, d.generator_inv, d.size_inv);
+        } else {
+#pragma omp parallel for schedule(static)
+            for (size_t i = 0; i < d.n; i++) x[i] = x[i] * d.size_inv;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- helpers for I/O
+template <class F> static void load_f(F& f, const u64* src);
+template <class T> static void load_fp(Fp<T>& f, const u64* src) { memcpy(f.l, src, sizeof(f.l)); }
+template <class T> static void load_any(Fp<T>& f, const u64* src) { load_fp(f, src); }
+template <class T> static void load_any(Fp2<T>& f, const u64* src) { load_fp(f.c0, src); load_fp(f.c1, src + T::N); }
+template <class T> static void store_any(const Fp<T>& f, u64* dst) { memcpy(dst, f.l, sizeof(f.l)); }
+template <class T> static void store_any(const Fp2<T>& f, u64* dst) { store_any(f.c0, dst); store_any(f.c1, dst + T::N); }
+
+template <class F>
+static int run_msm(const u64* bases_xy, const uint8_t* inf, const u64* scalars, size_t n, int num_bits, u64* out_xy,
+                   uint8_t* out_inf, int threads) {
+    constexpr int W = F::WORDS;
+    std::vector<Aff<F>> b(n);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        load_any(b[i].x, bases_xy + 2 * W * i);
+        load_any(b[i].y, bases_xy + 2 * W * i + W);
+        b[i].inf = inf ? inf[i] != 0 : false;
+    }
+    Aff<F> r = msm_arkworks<F>(b.data(), scalars, n, num_bits, threads);
+    if (r.inf) { memset(out_xy, 0, 2 * W * 8); *out_inf = 1; }
+    else { store_any(r.x, out_xy); store_any(r.y, out_xy + W); *out_inf = 0; }
+    return 0;
+}
+
+// P_i = (a0 + i*d) * G by chained Jacobian adds per thread chunk, each normalised with into_affine
+template <class F>
+static Jac<F> jac_mul_u64(const Aff<F>& g, u64 k) {
+    Jac<F> r = Jac<F>::zero();
+    for (int b = 63; b >= 0; b--) {
+        r.double_in_place();
+        if ((k >> b) & 1) r.add_assign_mixed(g);
+    }
+    return r;
+}
+template <class F>
+static int run_progression(const u64* gen_xy, u64 a0, u64 d, size_t n, u64* out_xy) {
+    constexpr int W = F::WORDS;
+    Aff<F> g;
+    load_any(g.x, gen_xy);
+    load_any(g.y, gen_xy + W);
+    g.inf = false;
+    Aff<F> D = jac_mul_u64(g, d).into_affine();
+    int nt = omp_get_max_threads();
+    size_t chunk = (n + nt - 1) / nt;
+    if (chunk == 0) chunk = 1;
+#pragma omp parallel for schedule(static, 1)
+    for (size_t start = 0; start < n; start += chunk) {
+        size_t end = std::min(n, start + chunk);
+        Jac<F> cur = jac_mul_u64(g, a0 + (u64)start * d);
+        for (size_t i = start; i < end; i++) {
+            Aff<F> a = cur.into_affine();
+            store_any(a.x, out_xy + 2 * W * i);
+            store_any(a.y, out_xy + 2 * W * i + W);
+            cur.add_assign_mixed(D);
+        }
+    }
+    return 0;
+}
+
+template <class T>
+static int run_ntt(u64* data, int log_n, int inverse, int coset, u64 generator, int two_adicity, int threads) {
+    Domain<Fp<T>> d;
+    if (!make_domain<T>(d, log_n, generator, two_adicity)) return -2;
+    if (threads > 0) omp_set_num_threads(threads);
+    ntt_arkworks(reinterpret_cast<Fp<T>*>(data), d, inverse, coset);
+    return 0;
+}
+
+template <class T>
+static int run_domain(int log_n, u64 generator, int two_adicity, u64* out /* 5 x N */) {
+    Domain<Fp<T>> d;
+    if (!make_domain<T>(d, log_n, generator, two_adicity)) return -2;
+    store_any(d.group_gen, out);
+    store_any(d.group_gen_inv, out + T::N);
+    store_any(d.size_inv, out + 2 * T::N);
+    store_any(d.generator, out + 3 * T::N);
+    store_any(d.generator_inv, out + 4 * T::N);
+    return 0;
+}
+
+extern "C" {
+// curve: 0 = BLS12-381, 1 = BN254 (same ids as include/zkm_b200.h).  group: 1 | 2.
+// Formats are arkworks': coordinates Montgomery LE u64 limbs, scalars canonical LE 4 x u64.
+int orc_msm(int curve, int group, const u64* bases_xy, const uint8_t* inf, const u64* scalars, size_t n, u64* out_xy,
+            uint8_t* out_inf, int threads) {
+    if (curve == 0 && group == 1) return run_msm<Fp<BlsFqTag>>(bases_xy, inf, scalars, n, 255, out_xy, out_inf, threads);
+    if (curve == 0 && group == 2) return run_msm<Fp2<BlsFqTag>>(bases_xy, inf, scalars, n, 255, out_xy, out_inf, threads);
+    if (curve == 1 && group == 1) return run_msm<Fp<BnFqTag>>(bases_xy, inf, scalars, n, 254, out_xy, out_inf, threads);
+    if (curve == 1 && group == 2) return run_msm<Fp2<BnFqTag>>(bases_xy, inf, scalars, n, 254, out_xy, out_inf, threads);
+    return -1;
+}
+int orc_ntt(int curve, u64* data, int log_n, int inverse, int coset, int threads) {
+    if (curve == 0) return run_ntt<BlsFrTag>(data, log_n, inverse, coset, 7, 32, threads);
+    if (curve == 1) return run_ntt<BnFrTag>(data, log_n, inverse, coset, 5, 28, threads);
+    return -1;
+}
+// out: group_gen, group_gen_inv, size_inv, generator, generator_inv  (Montgomery, 4 limbs each)
+int orc_domain(int curve, int log_n, u64* out) {
+    if (curve == 0) return run_domain<BlsFrTag>(log_n, 7, 32, out);
+    if (curve == 1) return run_domain<BnFrTag>(log_n, 5, 28, out);
+    return -1;
+}
+int orc_progression(int curve, int group, const u64* gen_xy, u64 a0, u64 d, size_t n, u64* out_xy) {
+    if (curve == 0 && group == 1) return run_progression<Fp<BlsFqTag>>(gen_xy, a0, d, n, out_xy);
+    if (curve == 0 && group == 2) return run_progression<Fp2<BlsFqTag>>(gen_xy, a0, d, n, out_xy);
+    if (curve == 1 && group == 1) return run_progression<Fp<BnFqTag>>(gen_xy, a0, d, n, out_xy);
+    if (curve == 1 && group == 2) return run_progression<Fp2<BnFqTag>>(gen_xy, a0, d, n, out_xy);
+    return -1;
+}
+// field: 0 bls fq, 1 bls fr, 2 bn fq, 3 bn fr.  op: 0 mul, 1 add, 2 sub, 3 inverse(a), 4 into_repr(a)
+int orc_field_op(int field, int op, const u64* a, const u64* b, u64* out) {
+#define ORC_FOP(T)                                                        \
+    {                                                                     \
+        Fp<T> x, y, r;                                                    \
+        load_fp(x, a);                                                    \
+        load_fp(y, b);                                                    \
+        switch (op) {                                                     \
+            case 0: r = x * y; break;                                     \
+            case 1: r = x + y; break;                                     \
+            case 2: r = x - y; break;                                     \
+            case 3: r = x.inverse(); break;                               \
+            case 4: x.into_repr(r.l); break;                              \
+            default: return -1;                                           \
+        }                                                                 \
+        store_any(r, out);                                                \
+        return 0;                                                         \
+    }
+    switch (field) {
+        case 0: ORC_FOP(BlsFqTag)
+        case 1: ORC_FOP(BlsFrTag)
+        case 2: ORC_FOP(BnFqTag)
+        case 3: ORC_FOP(BnFrTag)
+    }
+    return -1;
+}
+int orc_num_threads(void) { return omp_get_max_threads(); }
+int orc_msm_window_bits(size_t n) { return n < 32 ? 3 : (int)ln_without_floats(n) + 2; }
+}
