@@ -1,0 +1,133 @@
+/* zkm_b200.h -- C ABI of the B200-native proving backend for zkMember's hot paths.
+ *
+ * The boundary does not exist in the reference: zkMember (/root/reference) calls MSM and FFT
+ * statically through un-vendored arkworks 0.3.0 crates (pins: /root/reference/Cargo.lock:179-180
+ * ark-ec, :338-339 ark-poly, :229-230 ark-ff), reached from /root/reference/benches/groth16.rs:115
+ * (Groth16::prove) and /root/reference/benches/marlin.rs:202,311 (Marlin::prove).  Each entry
+ * point below names the upstream function it replaces; INTEGRATION.md shows the Rust `-sys`
+ * binding and the [patch.crates-io] forks that route the generic arkworks code here.
+ *
+ * Data formats are arkworks' own, byte for byte:
+ *   field element : little-endian u64 limbs, Montgomery form, R = 2^(64*limbs)  (ark-ff Fp256/Fp384)
+ *   scalar        : 4 x u64 little-endian, canonical (Fr::into_repr() -> BigInteger256)
+ *   G1 affine     : x, y                      (2 * L64 words)  + a separate infinity byte per point
+ *   G2 affine     : x.c0, x.c1, y.c0, y.c1    (4 * L64 words)  + infinity byte
+ *   L64 = 6 for BLS12-381 Fq, 4 for BN254 Fq.  Fr is 4 words for both curves.
+ *
+ * Every function returns 0 on success or a negative ZKM_ERR_* code; the message of the last
+ * failure on the calling thread is available from zkm_last_error().  Nothing throws, aborts or
+ * calls back.  There is NO CPU fallback: without a usable CUDA device every compute entry point
+ * fails with ZKM_ERR_CUDA.
+ *
+ * Threading: one process per GPU is the intended deployment (zkm_init(device) once, then any
+ * thread may call).  Calls on one device are serialised by an internal mutex.
+ *
+ * Ownership: the caller owns every buffer it passes; the library reads inputs / writes outputs
+ * during the call only and retains nothing except bases registered with zkm_bases_register*.
+ */
+#ifndef ZKM_B200_H
+#define ZKM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKM_CURVE_BLS12_381 0
+#define ZKM_CURVE_BN254 1
+
+#define ZKM_OK 0
+#define ZKM_ERR_ARG (-1)          /* bad curve / group / size / null pointer */
+#define ZKM_ERR_CUDA (-2)         /* CUDA runtime failure or no device */
+#define ZKM_ERR_NOT_INIT (-3)     /* zkm_init() has not succeeded */
+#define ZKM_ERR_DOMAIN (-4)       /* log_n exceeds the field's two-adicity (upstream: Domain::new -> None) */
+#define ZKM_ERR_SCALAR_RANGE (-5) /* a scalar has bits at or above the modulus width (not canonical) */
+#define ZKM_ERR_HANDLE (-6)       /* unknown / released bases handle, or range outside the registration */
+#define ZKM_ERR_OOM (-7)          /* device or pinned-host allocation failed */
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+int32_t zkm_init(int32_t device);   /* bind this process to CUDA device `device`; idempotent */
+void zkm_shutdown(void);            /* release every device allocation and registered bases */
+const char* zkm_last_error(void);   /* thread-local, never NULL */
+int32_t zkm_device_count(void);     /* visible CUDA devices (0 when none / no driver) */
+const char* zkm_version(void);
+
+/* ---- variable-base MSM ----------------------------------------------------------------------
+ * Replaces ark_ec::msm::VariableBaseMSM::multi_scalar_mul (ark-ec 0.3.0 src/msm/variable_base.rs)
+ * followed by into_affine() (src/models/short_weierstrass_jacobian.rs): computes
+ * sum_{i<n} scalars[i] * bases[i] and returns the unique normalised affine point.  The caller has
+ * already taken n = min(len(bases), len(scalars)) as upstream does.  Zero scalars and infinity
+ * bases are legal; n = 0 gives the identity (out_inf = 1, out_xy = arkworks' zero: x = 0, y = 1).
+ * `infinity` may be NULL (no point at infinity among the bases).  All pointers are HOST pointers. */
+int32_t zkm_msm_g1(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity,
+                   const uint64_t* scalars, size_t n, uint64_t* out_xy, uint8_t* out_inf);
+int32_t zkm_msm_g2(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity,
+                   const uint64_t* scalars, size_t n, uint64_t* out_xy, uint8_t* out_inf);
+
+/* Proving-key / SRS vectors are static across proofs (pk reuse at
+ * /root/reference/benches/groth16.rs:107-115): upload them once and refer to them by handle. */
+int32_t zkm_bases_register(int32_t curve, int32_t group /* 1 | 2 */, const uint64_t* bases_xy,
+                           const uint8_t* infinity, size_t n, uint64_t* handle_out);
+int32_t zkm_bases_release(uint64_t handle);
+/* MSM over bases[offset .. offset + n) of a registration (KZG10::commit's powers_of_g[z..] slice,
+ * ark-poly-commit 0.3.0 src/kzg10/mod.rs); scalars and outputs are HOST pointers. */
+int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scalars, size_t n,
+                           uint64_t* out_xy, uint8_t* out_inf);
+
+/* ---- radix-2 NTT ------------------------------------------------------------------------------
+ * Replaces ark_poly::Radix2EvaluationDomain::{fft_in_place, ifft_in_place, coset_fft_in_place,
+ * coset_ifft_in_place} (ark-poly 0.3.0 src/domain/radix2/{mod,fft}.rs, src/domain/mod.rs) on the
+ * scalar field Fr of `curve`.  `data` holds 2^log_n Montgomery elements, natural order in and out,
+ * transformed in place (the caller has already resized to the domain size as upstream does).
+ *   inverse = 0, coset = 0 : fft           X[k] = sum_j x[j] w^(jk)
+ *   inverse = 0, coset = 1 : coset_fft     x[j] *= g^j first, g = Fr::multiplicative_generator()
+ *   inverse = 1, coset = 0 : ifft          includes the multiplication by size_inv
+ *   inverse = 1, coset = 1 : coset_ifft    ifft, then x[j] *= g^-j
+ * log_n > TWO_ADICITY (32 for BLS12-381 Fr, 28 for BN254 Fr) fails with ZKM_ERR_DOMAIN. */
+int32_t zkm_ntt(int32_t curve, uint64_t* data, uint32_t log_n, int32_t inverse, int32_t coset);
+
+/* Radix2EvaluationDomain::new: the five domain constants, Montgomery, 4 words each:
+ * group_gen, group_gen_inv, size_inv, generator (= GENERATOR), generator_inv. */
+int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5x4);
+
+/* ---- device-resident variants ---------------------------------------------------------------
+ * Same operations with DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL = the
+ * library's own stream) without host synchronisation unless stated.  They are what a
+ * device-resident prover (witness map feeding the h-query MSM) chains together, and what
+ * bench.py times as the kernel-only figure. */
+int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n,
+                       int32_t inverse, int32_t coset, void* stream);
+/* d_out: 2 * W words (affine, Montgomery) followed by one u64 infinity flag (0 | 1).
+ * Synchronises once internally (bucket-occupancy read-back that sizes the reduction tree). */
+int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n,
+                                  uint64_t* d_out, void* stream);
+/* Adopt (copy) bases that already live in device memory. */
+int32_t zkm_bases_register_device(int32_t curve, int32_t group, const uint64_t* d_bases_xy,
+                                  const uint8_t* d_infinity, size_t n, uint64_t* handle_out);
+/* Sum of m affine points given as m records of (2 * W words + 1 flag word), e.g. the per-GPU
+ * partial results of a range-sharded MSM gathered on one device.  d_out has the same record
+ * format.  Replaces the final GroupProjective additions of the sharded caller. */
+int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_points, size_t m,
+                              uint64_t* d_out, void* stream);
+
+/* ---- tuning / introspection ------------------------------------------------------------------ */
+/* key: "msm_window_bits" (0 = automatic), "msm_chunk" (points per accumulation task, 0 = auto),
+ * "ntt_max_radix_log" (3..12).  Unknown keys fail with ZKM_ERR_ARG. */
+int32_t zkm_set_option(const char* key, int64_t value);
+/* Kernel launches issued by this library since the last call with reset != 0. */
+uint64_t zkm_launch_count(int32_t reset);
+/* Window bits the automatic choice uses for an n-point MSM (for reports). */
+int32_t zkm_msm_window_bits(int32_t curve, int32_t group, size_t n);
+
+/* ---- synthetic inputs (bench / tests) ------------------------------------------
+ * Bases with known discrete logs P_i = (a0 + i * d) * G written to device memory as n affine
+ * records of 2 * W words (no infinity among them when a0 + i*d != 0 mod r). */
+int32_t zkm_testgen_progression_device(int32_t curve, int32_t group, uint64_t a0, uint64_t d,
+                                       size_t n, uint64_t* d_bases_xy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKM_B200_H */

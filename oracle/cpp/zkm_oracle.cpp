@@ -518,8 +518,10 @@ static int run_msm(const u64* bases_xy, const uint8_t* inf, const u64* scalars, 
         b[i].inf = inf ? inf[i] != 0 : false;
     }
     Aff<F> r = msm_arkworks<F>(b.data(), scalars, n, num_bits, threads);
-    if (r.inf) { memset(out_xy, 0, 2 * W * 8); *out_inf = 1; }
-    else { store_any(r.x, out_xy); store_any(r.y, out_xy + W); *out_inf = 0; }
+    // the identity is encoded like ark-ec's GroupAffine::zero(): x = 0, y = 1, infinity = true
+    store_any(r.x, out_xy);
+    store_any(r.y, out_xy + W);
+    *out_inf = r.inf ? 1 : 0;
     return 0;
 }
 

@@ -1,0 +1,286 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of
+libzkm_b200.so (via the ctypes host layer) and is compared bit-for-bit with the CPU oracle -- the
+C++ restatement of the arkworks 0.3.0 algorithms (oracle/cpp) and the exact big-int definitions
+(oracle/py).  Integer work: the bar is byte equality."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import capi
+from oracle.py import exact
+from oracle.py.params import BLS12_381, BN254
+
+pytestmark = pytest.mark.gpu
+
+CURVES = [BLS12_381, BN254]
+MODES = [(False, False), (True, False), (False, True), (True, True)]
+
+
+@pytest.fixture(scope="module")
+def zkm():
+    import zkmember_b200 as z
+    z.init(0)
+    return z
+
+
+# ----------------------------------------------------------------------------------------- NTT
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 18])
+def test_ntt_matches_oracle(zkm, curve, log_n):
+    n = 1 << log_n
+    data = capi.random_field_elements(curve.curve_id, n, seed=0x5EED1000 + log_n)
+    dom = zkm.Radix2EvaluationDomain(curve.name, log_n)
+    for inverse, coset in MODES:
+        want = capi.ntt(curve.curve_id, data, inverse, coset)
+        fn = {(False, False): dom.fft, (True, False): dom.ifft, (False, True): dom.coset_fft, (True, True): dom.coset_ifft}[(inverse, coset)]
+        got = fn(data)
+        assert np.array_equal(got, want), "log_n=%d inverse=%s coset=%s" % (log_n, inverse, coset)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("radix", [6, 8, 11, 12])
+def test_ntt_pass_plans(zkm, curve, radix):
+    """Different pass decompositions (1, 2, 3 passes; tiles up to 2^12) give the same bytes."""
+    zkm.set_option("ntt_max_radix_log", radix)
+    try:
+        for log_n in (12, 14, 17):
+            data = capi.random_field_elements(curve.curve_id, 1 << log_n, seed=77 + log_n)
+            dom = zkm.Radix2EvaluationDomain(curve.name, log_n)
+            assert np.array_equal(dom.fft(data), capi.ntt(curve.curve_id, data))
+            assert np.array_equal(dom.coset_ifft(data), capi.ntt(curve.curve_id, data, True, True))
+    finally:
+        zkm.set_option("ntt_max_radix_log", 10)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_ntt_zero_padding_and_definition(zkm, curve):
+    """fft() resizes short inputs with zeros like upstream; outputs equal the O(n^2) definition."""
+    fr = curve.fr
+    x = [3, 1, 4, 1, 5]
+    dom = zkm.Radix2EvaluationDomain.new(len(x), curve.name)
+    assert dom.size == 8
+    data = capi.ints_to_limbs([fr.to_mont(v) for v in x], 4)
+    got = capi.limbs_to_ints(dom.fft(data))
+    want = exact.ntt_def(fr, x + [0, 0, 0])
+    assert got == [fr.to_mont(v) for v in want]
+    got = capi.limbs_to_ints(dom.coset_fft(data))
+    assert got == [fr.to_mont(v) for v in exact.ntt_def(fr, x + [0, 0, 0], coset=True)]
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_ntt_large_roundtrip_linearity_horner(zkm, curve):
+    """Size-independent properties at 2^22: ifft(fft(x)) == x, coset round trip, linearity, and Horner
+    spot checks of a few outputs with exact big-int arithmetic."""
+    fr = curve.fr
+    log_n = 22
+    n = 1 << log_n
+    dom = zkm.Radix2EvaluationDomain(curve.name, log_n)
+    x = capi.random_field_elements(curve.curve_id, n, seed=0x5EED1000 + log_n)
+    ev = dom.fft(x)
+    assert np.array_equal(dom.ifft(ev), x)
+    cev = dom.coset_fft(x)
+    assert np.array_equal(dom.coset_ifft(cev), x)
+    coeffs = [fr.from_mont(v) for v in capi.limbs_to_ints(x[:4096])]
+    # fft of the truncated polynomial, checked by Horner at three domain points
+    xs = np.zeros_like(x)
+    xs[:4096] = x[:4096]
+    evs = dom.fft(xs)
+    d = exact.domain_constants(fr, log_n)
+    for k in (1, 12345, n - 1):
+        pt = pow(d["group_gen"], k, fr.modulus)
+        assert fr.from_mont(capi.limbs_to_ints(evs[k:k + 1])[0]) == exact.horner_eval(fr, coeffs, pt)
+    # linearity: fft(x) == fft(xs) + fft(x - xs), spot-checked on a slice with exact arithmetic
+    xr = x.copy()
+    xr[:4096] = 0
+    evr = dom.fft(xr)
+    for k in (0, 7, n // 3):
+        a = fr.from_mont(capi.limbs_to_ints(evs[k:k + 1])[0])
+        b = fr.from_mont(capi.limbs_to_ints(evr[k:k + 1])[0])
+        assert (a + b) % fr.modulus == fr.from_mont(capi.limbs_to_ints(ev[k:k + 1])[0])
+
+
+def test_ntt_domain_errors(zkm):
+    assert zkm.Radix2EvaluationDomain.new((1 << 28) + 1, "bn254") is None      # upstream: new() -> None
+    assert zkm.Radix2EvaluationDomain.new(1 << 28, "bn254") is not None
+    with pytest.raises(zkm.DomainError):
+        zkm.Radix2EvaluationDomain("bn254", 29)
+    for curve in CURVES:
+        for log_n in (0, 5, 16, curve.fr.two_adicity):
+            d = zkm.Radix2EvaluationDomain(curve.name, log_n)
+            e = exact.domain_constants(curve.fr, log_n)
+            for name in ("group_gen", "group_gen_inv", "size_inv", "generator_inv"):
+                assert capi.limbs_to_ints(getattr(d, name)[None, :])[0] == curve.fr.to_mont(e[name]), (log_n, name)
+
+
+# ----------------------------------------------------------------------------------------- MSM
+def _check_point(curve, g, got, want_xy, want_inf):
+    assert got.infinity == bool(want_inf)
+    assert np.array_equal(got.xy, want_xy), (got.xy, want_xy)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("g", [1, 2])
+@pytest.mark.parametrize("n,kind", [(0, "uniform"), (1, "uniform"), (2, "uniform"), (7, "uniform"), (33, "small"),
+                                    (100, "witness"), (1000, "uniform"), (4096, "uniform"), (5000, "witness")])
+def test_msm_matches_oracle(zkm, curve, g, n, kind):
+    bases = capi.progression(curve.curve_id, g, 11 + n, 7, n)
+    scal = capi.random_scalars(curve.curve_id, n, seed=n * 10 + g, kind=kind)
+    inf = np.zeros(n, dtype=np.uint8)
+    if n >= 7:
+        inf[2] = 1                    # point at infinity among the bases
+        bases[4] = bases[3]           # repeated point
+        W = bases.shape[1] // 2
+        G = exact.Group(curve, g)
+        P5 = exact.point_from_bytes(curve, g, bases[5].tobytes(), 0)
+        b, _ = exact.point_to_bytes(curve, g, G.neg(P5))
+        bases[6] = np.frombuffer(b, dtype=np.uint64)   # P and -P with equal scalars cancel
+        scal[6] = scal[5]
+    want_xy, want_inf = capi.msm(curve.curve_id, g, bases, scal, inf)
+    got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal, curve=curve.name, group=g, infinity=inf)
+    _check_point(curve, g, got, want_xy, want_inf)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("kind", ["uniform", "witness"])
+def test_msm_g1_2p16_matches_oracle(zkm, curve, kind):
+    n = 1 << 16
+    bases = capi.progression(curve.curve_id, 1, 0xABCDEF, 0x1357, n)
+    scal = capi.random_scalars(curve.curve_id, n, seed=0x5EED0000 + 16, kind=kind)
+    inf = np.zeros(n, dtype=np.uint8)
+    rng = np.random.default_rng(5)
+    inf[rng.integers(0, n, 16)] = 1
+    dup = rng.integers(1, n, 16)
+    bases[dup] = bases[dup - 1]
+    want_xy, want_inf = capi.msm(curve.curve_id, 1, bases, scal, inf)
+    got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal, curve=curve.name, group=1, infinity=inf)
+    _check_point(curve, 1, got, want_xy, want_inf)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("c_bits", [4, 9, 13, 16])
+def test_msm_window_sizes_agree(zkm, curve, c_bits):
+    """Any window size / chunk length gives the same affine point (the result is unique)."""
+    n = 3000
+    bases = capi.progression(curve.curve_id, 1, 99, 5, n)
+    scal = capi.random_scalars(curve.curve_id, n, seed=c_bits, kind="uniform")
+    want_xy, want_inf = capi.msm(curve.curve_id, 1, bases, scal)
+    zkm.set_option("msm_window_bits", c_bits)
+    zkm.set_option("msm_chunk", 7)
+    try:
+        got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal, curve=curve.name, group=1)
+    finally:
+        zkm.set_option("msm_window_bits", 0)
+        zkm.set_option("msm_chunk", 0)
+    _check_point(curve, 1, got, want_xy, want_inf)
+
+
+def test_msm_all_equal_scalars_deep_fold(zkm):
+    """Every point lands in the same bucket of each window: exercises the multi-level fold."""
+    curve = BLS12_381
+    n = 20000
+    bases = capi.progression(curve.curve_id, 1, 1, 1, n)
+    scal = np.tile(np.array([[0x0123456789ABCDEF, 0x1111, 0, 0]], dtype=np.uint64), (n, 1))
+    want_xy, want_inf = capi.msm(curve.curve_id, 1, bases, scal)
+    got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal, curve=curve.name, group=1)
+    _check_point(curve, 1, got, want_xy, want_inf)
+    # and the all-ones witness (the scalar==1 fast path upstream)
+    scal1 = np.zeros((n, 4), dtype=np.uint64)
+    scal1[:, 0] = 1
+    want_xy, want_inf = capi.msm(curve.curve_id, 1, bases, scal1)
+    got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal1, curve=curve.name, group=1)
+    _check_point(curve, 1, got, want_xy, want_inf)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_msm_registered_slices(zkm, curve):
+    """KZG10::commit's powers_of_g[z..] slicing: MSM over a sub-range of registered bases."""
+    n = 2048
+    bases = capi.progression(curve.curve_id, 1, 3, 11, n)
+    reg = zkm.RegisteredBases(curve.name, 1, bases)
+    try:
+        for off, m in ((0, n), (5, 1000), (n - 1, 1), (100, 0)):
+            scal = capi.random_scalars(curve.curve_id, m, seed=off + m)
+            want_xy, want_inf = capi.msm(curve.curve_id, 1, bases[off:off + m], scal)
+            got = reg.msm(scal, offset=off)
+            _check_point(curve, 1, got, want_xy, want_inf)
+        with pytest.raises(zkm.ZkmError):
+            reg.msm(capi.random_scalars(curve.curve_id, 10, 1), offset=n - 5, n=10)
+    finally:
+        reg.release()
+    with pytest.raises(zkm.ZkmError):
+        reg2 = zkm.RegisteredBases(curve.name, 1, bases[:4])
+        reg2.release()
+        reg2.handle = 12345
+        reg2.msm(capi.random_scalars(curve.curve_id, 4, 1))
+
+
+def test_msm_rejects_non_canonical_scalar(zkm):
+    bases = capi.progression(0, 1, 1, 1, 8)
+    scal = capi.random_scalars(0, 8, 1)
+    scal[3, 3] = 0xFFFFFFFFFFFFFFFF
+    with pytest.raises(zkm.ZkmError) as ei:
+        zkm.VariableBaseMSM.multi_scalar_mul(bases, scal)
+    assert ei.value.code == -5
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_msm_known_discrete_log_2p20(zkm, curve):
+    """Full-size property: with bases P_i = (a0 + i d) G generated on the device,
+    sum s_i P_i == (sum s_i (a0 + i d) mod r) G, checked with exact big-int arithmetic."""
+    import torch
+    n = 1 << 20
+    a0, d = 0x1234567, 0x89ABCDE
+    W = 6 if curve.curve_id == 0 else 4
+    dev = torch.device("cuda:0")
+    d_bases = torch.empty((n, 2 * W), dtype=torch.int64, device=dev)
+    L = zkm._lib.lib()
+    zkm._lib.check(L.zkm_testgen_progression_device(curve.curve_id, 1, a0, d, n, ctypes.c_void_p(d_bases.data_ptr()),
+                                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    # the generator itself is pinned against the oracle's chained-addition progression
+    head = d_bases[:64].cpu().numpy().view(np.uint64)
+    assert np.array_equal(head, capi.progression(curve.curve_id, 1, a0, d, 64))
+    reg = zkm.RegisteredBases.from_device(curve.name, 1, d_bases.data_ptr(), n)
+    scal = capi.random_scalars(curve.curve_id, n, seed=0x5EED0000 + 20)
+    got = reg.msm(scal)
+    reg.release()
+    r = curve.fr.modulus
+    s_int = scal.astype(object)
+    s_vals = s_int[:, 0] + (s_int[:, 1] << 64) + (s_int[:, 2] << 128) + (s_int[:, 3] << 192)
+    idx = np.arange(n, dtype=object)
+    k = int(np.sum(s_vals * (a0 + idx * d)) % r)
+    G = exact.Group(curve, 1)
+    want = G.mul(G.gen, k)
+    b, f = exact.point_to_bytes(curve, 1, want)
+    assert not got.infinity and got.xy.tobytes() == b
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("g", [1, 2])
+def test_points_sum_device(zkm, curve, g):
+    """The cross-GPU reduction step: sum of a handful of partial results."""
+    import torch
+    G = exact.Group(curve, g)
+    pts = G.progression(5, 9, 6)
+    pts[2] = None
+    pts[4] = pts[3]
+    W = curve.fq.limbs64 * g
+    rec = np.zeros((len(pts), 2 * W + 1), dtype=np.uint64)
+    for i, P in enumerate(pts):
+        b, f = exact.point_to_bytes(curve, g, P)
+        rec[i, :2 * W] = np.frombuffer(b, dtype=np.uint64)
+        rec[i, 2 * W] = f
+    d_in = torch.from_numpy(rec.view(np.int64)).cuda()
+    d_out = torch.zeros(2 * W + 1, dtype=torch.int64, device="cuda")
+    L = zkm._lib.lib()
+    zkm._lib.check(L.zkm_points_sum_device(curve.curve_id, g, ctypes.c_void_p(d_in.data_ptr()), len(pts),
+                                            ctypes.c_void_p(d_out.data_ptr()),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy().view(np.uint64)
+    want = None
+    for P in pts:
+        want = G.add(want, P)
+    b, f = exact.point_to_bytes(curve, g, want)
+    assert out[2 * W] == f and out[:2 * W].tobytes() == b

@@ -1,0 +1,352 @@
+// zkm_api.cu -- the C ABI of include/zkm_b200.h: context, error reporting, host<->device staging.
+// Every compute call ends in the CUDA kernels of zkm_ntt.cu / zkm_msm.cu; there is no CPU path.
+#include <stdarg.h>
+#include <string.h>
+
+#include "zkm_common.cuh"
+
+namespace zkm {
+
+static thread_local char t_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+static Context* g_ctx = nullptr;
+static std::mutex g_init_mu;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+Context* ctx() {
+    if (!g_ctx) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
+    return g_ctx;
+}
+
+template <class Fn>
+static int32_t guarded(Fn&& fn) {
+    try {
+        fn();
+        return ZKM_OK;
+    } catch (const ZkmError& e) {
+        cudaGetLastError();  // clear sticky-free errors so the next call starts clean
+        return e.code;
+    } catch (const std::exception& e) {
+        set_error("internal: %s", e.what());
+        return ZKM_ERR_CUDA;
+    } catch (...) {
+        set_error("internal: unknown exception");
+        return ZKM_ERR_CUDA;
+    }
+}
+
+static void check_curve_group(int curve, int group) {
+    if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+    if (group != 1 && group != 2) ZKM_FAIL(ZKM_ERR_ARG, "group must be 1 or 2, got %d", group);
+}
+
+// host -> device through the copy engine; pageable memory is fine (driver stages it)
+static void h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes) ZKM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+}
+
+static void msm_host(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* scalars,
+                     size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+    if (!out_xy || !out_inf) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
+    if (n && !scalars) ZKM_FAIL(ZKM_ERR_ARG, "null scalars");
+    const int W = coord_words(curve, group);
+    uint64_t* d_scal = (uint64_t*)c->io_scalars.get((n ? n : 1) * 32);
+    uint64_t* d_out = (uint64_t*)c->io_out.get((2 * W + 1) * 8);
+    h2d(d_scal, scalars, n * 32, c->stream);
+    msm_run(c, curve, group, d_bases, d_inf, d_scal, n, d_out, c->stream);
+    uint64_t* h = (uint64_t*)c->pin_in.get((2 * W + 1) * 8);
+    ZKM_CUDA(cudaMemcpyAsync(h, d_out, (2 * W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZKM_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(out_xy, h, 2 * W * 8);
+    *out_inf = h[2 * W] ? 1 : 0;
+}
+
+static int32_t msm_direct(int32_t curve, int group, const uint64_t* bases_xy, const uint8_t* infinity,
+                          const uint64_t* scalars, size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+    return guarded([&] {
+        Context* c = ctx();
+        check_curve_group(curve, group);
+        if (n && !bases_xy) ZKM_FAIL(ZKM_ERR_ARG, "null bases");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        const int W = coord_words(curve, group);
+        void* d_bases = c->io_bases.get((n ? n : 1) * 2 * W * 8);
+        uint8_t* d_inf = nullptr;
+        h2d(d_bases, bases_xy, n * 2 * W * 8, c->stream);
+        if (infinity) {
+            d_inf = (uint8_t*)c->io_inf.get(n ? n : 1);
+            h2d(d_inf, infinity, n, c->stream);
+        }
+        msm_host(c, curve, group, d_bases, d_inf, scalars, n, out_xy, out_inf);
+    });
+}
+
+}  // namespace zkm
+
+using namespace zkm;
+
+extern "C" {
+
+const char* zkm_last_error(void) { return t_err; }
+const char* zkm_version(void) { return "zkmember-b200 0.1 (sm_100a)"; }
+
+int32_t zkm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t zkm_init(int32_t device) {
+    return guarded([&] {
+        std::lock_guard<std::mutex> lk(g_init_mu);
+        if (g_ctx) {
+            if (g_ctx->device != device) ZKM_FAIL(ZKM_ERR_ARG, "already bound to device %d (one process per GPU)", g_ctx->device);
+            return;
+        }
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            ZKM_FAIL(ZKM_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        }
+        if (device < 0 || device >= count) ZKM_FAIL(ZKM_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
+        ZKM_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        ZKM_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) ZKM_FAIL(ZKM_ERR_CUDA, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
+        Context* c = new Context();
+        c->device = device;
+        c->sm_count = prop.multiProcessorCount;
+        ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        g_ctx = c;
+    });
+}
+
+void zkm_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    Context* c = g_ctx;
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    ntt_release(c);
+    for (auto& b : c->ws) b.release();
+    c->io_scalars.release();
+    c->io_bases.release();
+    c->io_inf.release();
+    c->io_out.release();
+    c->pin_in.release();
+    c->pin_out.release();
+    for (auto& kv : c->bases) {
+        cudaFree(kv.second.d_xy);
+        if (kv.second.d_inf) cudaFree(kv.second.d_inf);
+    }
+    c->bases.clear();
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    g_ctx = nullptr;
+    delete c;
+}
+
+int32_t zkm_msm_g1(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity, const uint64_t* scalars, size_t n,
+                   uint64_t* out_xy, uint8_t* out_inf) {
+    return msm_direct(curve, 1, bases_xy, infinity, scalars, n, out_xy, out_inf);
+}
+int32_t zkm_msm_g2(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity, const uint64_t* scalars, size_t n,
+                   uint64_t* out_xy, uint8_t* out_inf) {
+    return msm_direct(curve, 2, bases_xy, infinity, scalars, n, out_xy, out_inf);
+}
+
+static int32_t register_impl(int32_t curve, int32_t group, const uint64_t* xy, const uint8_t* inf, size_t n,
+                             uint64_t* handle_out, cudaMemcpyKind kind) {
+    return guarded([&] {
+        Context* c = ctx();
+        check_curve_group(curve, group);
+        if (!handle_out) ZKM_FAIL(ZKM_ERR_ARG, "null handle_out");
+        if (n && !xy) ZKM_FAIL(ZKM_ERR_ARG, "null bases");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        BasesReg r;
+        r.curve = curve;
+        r.group = group;
+        r.n = n;
+        const size_t bytes = n * 2 * coord_words(curve, group) * 8;
+        ZKM_CUDA(cudaMalloc(&r.d_xy, bytes ? bytes : 16));
+        if (bytes) ZKM_CUDA(cudaMemcpyAsync(r.d_xy, xy, bytes, kind, c->stream));
+        if (inf) {
+            ZKM_CUDA(cudaMalloc((void**)&r.d_inf, n ? n : 16));
+            if (n) ZKM_CUDA(cudaMemcpyAsync(r.d_inf, inf, n, kind, c->stream));
+        }
+        ZKM_CUDA(cudaStreamSynchronize(c->stream));
+        uint64_t h = c->next_handle++;
+        c->bases[h] = r;
+        *handle_out = h;
+    });
+}
+
+int32_t zkm_bases_register(int32_t curve, int32_t group, const uint64_t* bases_xy, const uint8_t* infinity, size_t n,
+                           uint64_t* handle_out) {
+    return register_impl(curve, group, bases_xy, infinity, n, handle_out, cudaMemcpyHostToDevice);
+}
+int32_t zkm_bases_register_device(int32_t curve, int32_t group, const uint64_t* d_bases_xy, const uint8_t* d_infinity,
+                                  size_t n, uint64_t* handle_out) {
+    return register_impl(curve, group, d_bases_xy, d_infinity, n, handle_out, cudaMemcpyDeviceToDevice);
+}
+
+int32_t zkm_bases_release(uint64_t handle) {
+    return guarded([&] {
+        Context* c = ctx();
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto it = c->bases.find(handle);
+        if (it == c->bases.end()) ZKM_FAIL(ZKM_ERR_HANDLE, "unknown bases handle %llu", (unsigned long long)handle);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        ZKM_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(it->second.d_xy);
+        if (it->second.d_inf) cudaFree(it->second.d_inf);
+        c->bases.erase(it);
+    });
+}
+
+static const BasesReg& lookup(Context* c, uint64_t handle, size_t offset, size_t n) {
+    auto it = c->bases.find(handle);
+    if (it == c->bases.end()) ZKM_FAIL(ZKM_ERR_HANDLE, "unknown bases handle %llu", (unsigned long long)handle);
+    if (offset > it->second.n || n > it->second.n - offset)
+        ZKM_FAIL(ZKM_ERR_HANDLE, "range [%zu, %zu) outside the %zu registered bases", offset, offset + n, it->second.n);
+    return it->second;
+}
+
+int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scalars, size_t n, uint64_t* out_xy,
+                           uint8_t* out_inf) {
+    return guarded([&] {
+        Context* c = ctx();
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        const BasesReg& r = lookup(c, handle, offset, n);
+        const size_t rec = 2 * coord_words(r.curve, r.group) * 8;
+        msm_host(c, r.curve, r.group, (const char*)r.d_xy + offset * rec, r.d_inf ? r.d_inf + offset : nullptr, scalars, n,
+                 out_xy, out_inf);
+    });
+}
+
+int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n, uint64_t* d_out,
+                                  void* stream) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (!d_out || (n && !d_scalars)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        const BasesReg& r = lookup(c, handle, offset, n);
+        const size_t rec = 2 * coord_words(r.curve, r.group) * 8;
+        cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+        msm_run(c, r.curve, r.group, (const char*)r.d_xy + offset * rec, r.d_inf ? r.d_inf + offset : nullptr, d_scalars, n,
+                d_out, s);
+    });
+}
+
+int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_points, size_t m, uint64_t* d_out,
+                              void* stream) {
+    return guarded([&] {
+        Context* c = ctx();
+        check_curve_group(curve, group);
+        if (!d_out || (m && !d_points)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        points_sum_run(c, curve, group, d_points, m, d_out, stream ? (cudaStream_t)stream : c->stream);
+    });
+}
+
+int32_t zkm_ntt(int32_t curve, uint64_t* data, uint32_t log_n, int32_t inverse, int32_t coset) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+        if (!data) ZKM_FAIL(ZKM_ERR_ARG, "null data");
+        const int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
+        if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
+        if (log_n > 30) ZKM_FAIL(ZKM_ERR_ARG, "log_n %u: domains above 2^30 are not supported by this build", log_n);
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        const size_t bytes = (size_t)32 << log_n;
+        uint64_t* d_a = (uint64_t*)c->io_scalars.get(bytes);
+        uint64_t* d_b = (uint64_t*)c->ntt_b.get(bytes);
+        h2d(d_a, data, bytes, c->stream);
+        ntt_run(c, curve, d_a, d_b, log_n, inverse != 0, coset != 0, c->stream);
+        ZKM_CUDA(cudaMemcpyAsync(data, d_b, bytes, cudaMemcpyDeviceToHost, c->stream));
+        ZKM_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int32_t inverse,
+                       int32_t coset, void* stream) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (!d_in || !d_out) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        ntt_run(c, curve, d_in, d_out, log_n, inverse != 0, coset != 0, stream ? (cudaStream_t)stream : c->stream);
+    });
+}
+
+int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5x4) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (!out5x4) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        ntt_domain_constants(curve, log_n, out5x4);
+    });
+}
+
+int32_t zkm_set_option(const char* key, int64_t value) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (!key) ZKM_FAIL(ZKM_ERR_ARG, "null key");
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!strcmp(key, "msm_window_bits")) {
+            if (value < 0 || value > 24) ZKM_FAIL(ZKM_ERR_ARG, "msm_window_bits must be 0 (auto) or 2..24");
+            c->opt.msm_window_bits = (int)value;
+        } else if (!strcmp(key, "msm_chunk")) {
+            if (value < 0 || value > 1024) ZKM_FAIL(ZKM_ERR_ARG, "msm_chunk must be 0 (auto) or 1..1024");
+            c->opt.msm_chunk = (int)value;
+        } else if (!strcmp(key, "ntt_max_radix_log")) {
+            if (value < 6 || value > 12) ZKM_FAIL(ZKM_ERR_ARG, "ntt_max_radix_log must be 6..12");
+            c->opt.ntt_max_radix_log = (int)value;
+        } else {
+            ZKM_FAIL(ZKM_ERR_ARG, "unknown option '%s'", key);
+        }
+    });
+}
+
+uint64_t zkm_launch_count(int32_t reset) {
+    uint64_t v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+int32_t zkm_msm_window_bits(int32_t curve, int32_t group, size_t n) {
+    if (g_ctx && g_ctx->opt.msm_window_bits > 0) return g_ctx->opt.msm_window_bits;
+    return msm_auto_window_bits(curve, group, n);
+}
+
+int32_t zkm_testgen_progression_device(int32_t curve, int32_t group, uint64_t a0, uint64_t d, size_t n,
+                                       uint64_t* d_bases_xy, void* stream) {
+    return guarded([&] {
+        Context* c = ctx();
+        check_curve_group(curve, group);
+        if (n && !d_bases_xy) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        testgen_progression(c, curve, group, a0, d, n, d_bases_xy, stream ? (cudaStream_t)stream : c->stream);
+    });
+}
+
+}  // extern "C"

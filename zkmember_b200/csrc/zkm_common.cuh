@@ -1,0 +1,200 @@
+// zkm_common.cuh -- process-wide context, error plumbing and launch helpers shared by the
+// NTT and MSM translation units.  Host-side C++ only wraps CUDA: there is no CPU compute path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/zkm_b200.h"
+#include "zkm_curve.cuh"
+
+namespace zkm {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+struct ZkmError {
+    int32_t code;
+};
+
+#define ZKM_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::zkm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            throw ::zkm::ZkmError{_e == cudaErrorMemoryAllocation ? ZKM_ERR_OOM : ZKM_ERR_CUDA};          \
+        }                                                                                     \
+    } while (0)
+
+#define ZKM_FAIL(code, ...)              \
+    do {                                 \
+        ::zkm::set_error(__VA_ARGS__);   \
+        throw ::zkm::ZkmError{code};     \
+    } while (0)
+
+// count + launch-check in one place
+#define ZKM_LAUNCH(kernel, grid, block, smem, stream, ...)                   \
+    do {                                                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
+        ::zkm::g_launches.fetch_add(1, std::memory_order_relaxed);           \
+        ZKM_CUDA(cudaGetLastError());                                        \
+    } while (0)
+
+// A growable device buffer (never shrinks; freed at shutdown).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* get(size_t bytes) {
+        if (bytes > cap) {
+            if (p) ZKM_CUDA(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+            size_t want = bytes + (bytes >> 3) + 256;
+            ZKM_CUDA(cudaMalloc(&p, want));
+            cap = want;
+        }
+        return p;
+    }
+    template <class T>
+    T* as(size_t count) { return reinterpret_cast<T*>(get(count * sizeof(T))); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* get(size_t bytes) {
+        if (bytes > cap) {
+            if (p) ZKM_CUDA(cudaFreeHost(p));
+            p = nullptr;
+            cap = 0;
+            ZKM_CUDA(cudaMallocHost(&p, bytes + 256));
+            cap = bytes + 256;
+        }
+        return p;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct BasesReg {
+    int curve, group;
+    size_t n;
+    void* d_xy = nullptr;     // n affine records, 2 * W * 8 bytes each
+    uint8_t* d_inf = nullptr; // n flags or nullptr
+};
+
+struct Options {
+    int msm_window_bits = 0;
+    int msm_chunk = 0;
+    int ntt_max_radix_log = 10;
+};
+
+struct Context {
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::mutex mu;
+    Options opt;
+    // NTT state
+    std::map<uint64_t, void*> twiddles;  // key -> device table
+    DevBuf ntt_a, ntt_b;
+    // MSM workspace
+    DevBuf ws[24];
+    DevBuf io_scalars, io_bases, io_inf, io_out;
+    PinnedBuf pin_in, pin_out;
+    std::map<uint64_t, BasesReg> bases;
+    uint64_t next_handle = 1;
+};
+
+Context* ctx();            // throws ZKM_ERR_NOT_INIT when zkm_init has not succeeded
+inline int coord_words(int curve, int group) {
+    return (curve == ZKM_CURVE_BLS12_381 ? 6 : 4) * (group == 2 ? 2 : 1);
+}
+
+// entry points implemented by the two compute translation units
+void ntt_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
+             cudaStream_t stream);
+void ntt_domain_constants(int curve, uint32_t log_n, uint64_t* out5x4_host);
+void ntt_release(Context* c);
+void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
+             size_t n, uint64_t* d_out, cudaStream_t stream);
+void points_sum_run(Context* c, int curve, int group, const uint64_t* d_points, size_t m, uint64_t* d_out,
+                    cudaStream_t stream);
+void testgen_progression(Context* c, int curve, int group, uint64_t a0, uint64_t d, size_t n, uint64_t* d_out,
+                         cudaStream_t stream);
+int msm_auto_window_bits(int curve, int group, size_t n);
+
+// 128-bit vectorised global access for field elements (N is a multiple of 4 limbs)
+template <class P>
+__device__ __forceinline__ Fp<P> ld_fp(const void* p) {
+    Fp<P> r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < P::N / 4; i++) {
+        uint4 v = __ldg(q + i);
+        r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+template <class P>
+__device__ __forceinline__ Fp<P> ld_fp_plain(const void* p) {  // coherent load (data written earlier in the same kernel)
+    Fp<P> r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < P::N / 4; i++) {
+        uint4 v = q[i];
+        r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+template <class P>
+__device__ __forceinline__ void st_fp(void* p, const Fp<P>& a) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < P::N / 4; i++) q[i] = make_uint4(a.l[4 * i], a.l[4 * i + 1], a.l[4 * i + 2], a.l[4 * i + 3]);
+}
+
+// generic coordinate (Fp or Fp2) access
+template <class F> struct CoordIO;
+template <class P> struct CoordIO<Fp<P>> {
+    static constexpr int BYTES = P::N * 4;
+    static __device__ __forceinline__ Fp<P> ld(const void* p) { return ld_fp<P>(p); }
+    static __device__ __forceinline__ Fp<P> ld_plain(const void* p) { return ld_fp_plain<P>(p); }
+    static __device__ __forceinline__ void st(void* p, const Fp<P>& a) { st_fp<P>(p, a); }
+};
+template <class P> struct CoordIO<Fp2<P>> {
+    static constexpr int BYTES = P::N * 8;
+    static __device__ __forceinline__ Fp2<P> ld(const void* p) {
+        Fp2<P> r;
+        r.c0 = ld_fp<P>(p);
+        r.c1 = ld_fp<P>(reinterpret_cast<const char*>(p) + P::N * 4);
+        return r;
+    }
+    static __device__ __forceinline__ Fp2<P> ld_plain(const void* p) {
+        Fp2<P> r;
+        r.c0 = ld_fp_plain<P>(p);
+        r.c1 = ld_fp_plain<P>(reinterpret_cast<const char*>(p) + P::N * 4);
+        return r;
+    }
+    static __device__ __forceinline__ void st(void* p, const Fp2<P>& a) {
+        st_fp<P>(p, a.c0);
+        st_fp<P>(reinterpret_cast<char*>(p) + P::N * 4, a.c1);
+    }
+};
+
+}  // namespace zkm

@@ -1,0 +1,313 @@
+// zkm_msm.cu -- variable-base multi-scalar multiplication (G1 and G2) on sm_100a.
+//
+// Replaces ark-ec 0.3.0 VariableBaseMSM::multi_scalar_mul (src/msm/variable_base.rs) plus the
+// final into_affine() (src/models/short_weierstrass_jacobian.rs); pin
+// /root/reference/Cargo.lock:179-180; reached from /root/reference/benches/groth16.rs:115
+// (ark-groth16 create_proof: h/l/a/b_g1 queries on G1, b_g2 query on G2) and from
+// /root/reference/benches/marlin.rs:202,311 (KZG10::commit).  The result is the unique normalised
+// affine point, so it is byte-identical to upstream's whatever the bucket schedule.
+//
+// Pipeline (a from-scratch design, not upstream's one-rayon-task-per-window loop):
+//   K2  k_msm_digits<0>   signed c-bit digits of every scalar, histogram of (window, |digit|) buckets
+//       scan              exclusive prefix sum of bucket sizes -> bucket offsets
+//   K3  k_msm_digits<1>   scatter (point index | sign) into digit-sorted bucket lists
+//       k_tasks_*         cut every bucket list into tasks of <= L entries, order tasks by length
+//   K4  k_accum_affine    one thread per task: XYZZ accumulator += affine base (madd-2008-s), bases
+//                         gathered with 128-bit loads; then k_accum_xyzz levels fold the per-task
+//                         partial sums until every bucket has one sum (keeps skewed inputs -- the
+//                         0/1-heavy Groth16 witness -- balanced without a special case)
+//   K5  k_bucket_reduce   running-sum reduction of each window in parallel slices, k_window_sum,
+//       k_msm_final       Horner combine over windows (c doublings each) and normalisation to affine
+// The integer pipe (Montgomery products) bounds K4; everything else is a few percent.  See DESIGN.md.
+#include <cub/device/device_scan.cuh>
+
+#include "zkm_msm.cuh"
+
+namespace zkm {
+
+// ---------------------------------------------------------------------------------- K2 / K3 digits
+
+// MODE 0: histogram into counts[K].  MODE 1: scatter (index | sign << 31) at cursor[key]++.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
+                                                    uint64_t n, MsmPlan pl, uint32_t* __restrict__ counts_or_cursor,
+                                                    uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (inf && inf[i]) continue;
+        const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * 8);
+        uint4 a = __ldg(sp), b = __ldg(sp + 1);
+        uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) continue;
+        const uint32_t mask = (1u << pl.c) - 1u;
+        uint64_t buf = 0;
+        int nb = 0, w = 0;
+        uint32_t carry = 0;
+#pragma unroll
+        for (int limb = 0; limb <= 8; limb++) {
+            if (limb < 8) {
+                buf |= (uint64_t)s[limb] << nb;
+                nb += 32;
+            } else {
+                nb = 64;  // flush: the rest of the buffer is zero extension
+            }
+            while (nb >= pl.c && w < pl.W) {
+                uint32_t d = ((uint32_t)buf & mask) + carry;
+                buf >>= pl.c;
+                nb -= pl.c;
+                uint32_t sign = 0;
+                carry = 0;
+                if (d > pl.B) {
+                    d = (1u << pl.c) - d;
+                    sign = 1;
+                    carry = 1;
+                }
+                if (d != 0) {
+                    uint32_t key = (uint32_t)w * pl.B + (d - 1);
+                    if (MODE == 0) {
+                        atomicAdd(&counts_or_cursor[key], 1u);
+                    } else {
+                        uint32_t pos = atomicAdd(&counts_or_cursor[key], 1u);
+                        idx_out[pos] = (uint32_t)i | (sign << 31);
+                    }
+                }
+                w++;
+            }
+        }
+        if (MODE == 0 && (buf != 0 || carry != 0)) atomicOr(&flags[1], 1u);  // scalar wider than the modulus
+    }
+}
+
+// ---------------------------------------------------------------------------------- task building
+// tpb[k] = ceil(cnt[k] / L); flags[0] = max cnt
+__global__ void k_tasks_count(const uint32_t* __restrict__ cnt, uint32_t K, uint32_t L, uint32_t* __restrict__ tpb,
+                              uint32_t* __restrict__ flags) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = 0;
+    if (k < K) {
+        v = cnt[k];
+        tpb[k] = (v + L - 1) / L;
+    } else if (k == K) {
+        tpb[k] = 0;
+    }
+    // block max then one atomic
+    __shared__ uint32_t smax;
+    if (threadIdx.x == 0) smax = 0;
+    __syncthreads();
+    uint32_t wmax = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && wmax) atomicMax(&smax, wmax);
+    __syncthreads();
+    if (threadIdx.x == 0 && smax && flags) atomicMax(&flags[0], smax);
+}
+
+// per task: owner bucket by binary search in tbase, (start, len), histogram of lengths
+__global__ void k_tasks_emit(const uint32_t* __restrict__ tbase, uint32_t K, const uint32_t* __restrict__ off,
+                             const uint32_t* __restrict__ cnt, uint32_t L, uint32_t* __restrict__ tstart,
+                             uint32_t* __restrict__ tlen, uint32_t* __restrict__ lenhist) {
+    extern __shared__ uint32_t sh_hist[];  // L + 1
+    for (uint32_t i = threadIdx.x; i <= L; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+    const uint32_t T = tbase[K];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        // largest k with tbase[k] <= t
+        uint32_t lo = 0, hi = K;  // tbase[lo] <= t < tbase[hi]
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (tbase[mid] <= t) lo = mid; else hi = mid;
+        }
+        uint32_t j = t - tbase[lo];
+        uint32_t c = cnt[lo];
+        uint32_t len = c - j * L;
+        if (len > L) len = L;
+        tstart[t] = off[lo] + j * L;
+        tlen[t] = len;
+        atomicAdd(&sh_hist[len], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= L; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(&lenhist[i], sh_hist[i]);
+}
+
+// cursor[len] = number of tasks strictly longer than len (descending-length order)
+__global__ void k_len_offsets(const uint32_t* __restrict__ lenhist, uint32_t L, uint32_t* __restrict__ cursor) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t acc = 0;
+    for (int len = (int)L; len >= 0; len--) {
+        cursor[len] = acc;
+        acc += lenhist[len];
+    }
+}
+
+__global__ void k_tasks_order(const uint32_t* __restrict__ tlen, const uint32_t* __restrict__ tbase, uint32_t K,
+                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    const uint32_t T = tbase[K];
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; t0 < T; t0 += gridDim.x * blockDim.x) {
+        uint32_t t = t0 + lane;
+        bool valid = t < T;
+        uint32_t len = valid ? tlen[t] : 0xffffffffu;
+        // warp-aggregated: lanes with equal len share one atomic
+        uint32_t peers = __match_any_sync(0xffffffffu, len);
+        uint32_t leader = __ffs(peers) - 1;
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (valid && lane == leader) base = atomicAdd(&cursor[len], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) order[base + rank] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------- host side
+static int windows_for(int scalar_bits, int c) { return (scalar_bits + 1 + c - 1) / c; }
+
+int msm_auto_window_bits(int curve, int group, size_t n) {
+    (void)group;
+    const int bits = curve == ZKM_CURVE_BLS12_381 ? 255 : 254;
+    if (n < 2) n = 2;
+    double best = 1e300;
+    int best_c = 4;
+    for (int c = 4; c <= 21; c++) {
+        double W = windows_for(bits, c);
+        double B = (double)(1u << (c - 1));
+        // madd = 10 products per (point, window); per bucket: ~3 full adds (14 products) for the
+        // running-sum reduction and the partial-sum fold, plus sort/bookkeeping
+        double cost = W * ((double)n * 10.0 + B * 50.0);
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
+}
+
+static const CurveOps* curve_ops(int curve, int group) {
+    if (curve == ZKM_CURVE_BLS12_381 && group == 1) return ops_g1_bls();
+    if (curve == ZKM_CURVE_BLS12_381 && group == 2) return ops_g2_bls();
+    if (curve == ZKM_CURVE_BN254 && group == 1) return ops_g1_bn();
+    if (curve == ZKM_CURVE_BN254 && group == 2) return ops_g2_bn();
+    ZKM_FAIL(ZKM_ERR_ARG, "unknown curve %d / group %d", curve, group);
+}
+
+enum WsSlot {
+    WS_COUNTS = 0, WS_OFF, WS_CURSOR, WS_IDX, WS_TPB_A, WS_TBASE_A, WS_TPB_B, WS_TBASE_B, WS_TSTART, WS_TLEN,
+    WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_PART_B, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP
+};
+
+static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t count, cudaStream_t s) {
+    size_t tmp_bytes = 0;
+    ZKM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)count, s));
+    void* tmp = c->ws[WS_CUBTMP].get(tmp_bytes ? tmp_bytes : 16);
+    ZKM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)count, s));
+}
+
+void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
+             size_t n, uint64_t* d_out, cudaStream_t s) {
+    const CurveOps* ops = curve_ops(curve, group);
+    if (n == 0) {
+        ops->write_identity(s, d_out);
+        return;
+    }
+    if (n >= (1ull << 31)) ZKM_FAIL(ZKM_ERR_ARG, "MSM of %zu points: at most 2^31 - 1 supported", n);
+    MsmPlan pl;
+    pl.scalar_bits = ops->scalar_bits;
+    pl.c = c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : msm_auto_window_bits(curve, group, n);
+    if (pl.c < 2) pl.c = 2;
+    if (pl.c > 24) pl.c = 24;
+    pl.W = windows_for(pl.scalar_bits, pl.c);
+    pl.B = 1u << (pl.c - 1);
+    pl.K = (uint32_t)pl.W * pl.B;
+    if ((double)n * pl.W >= 4.0e9)
+        ZKM_FAIL(ZKM_ERR_ARG, "MSM of %zu points x %d windows exceeds 2^32 bucket entries", n, pl.W);
+    const uint32_t K = pl.K;
+    const size_t entries = n * (size_t)pl.W;
+
+    // chunk lengths: level 1 (affine gather) and the fold levels (partial sums)
+    uint32_t L1;
+    if (c->opt.msm_chunk > 0) {
+        L1 = (uint32_t)c->opt.msm_chunk;
+    } else {
+        double per_thread = (double)entries / ((double)c->sm_count * 256.0 * 4.0);
+        L1 = per_thread < 16 ? 16u : (per_thread > 256 ? 256u : (uint32_t)per_thread);
+    }
+    if (L1 > 1024) L1 = 1024;
+    const uint32_t L2 = 16;
+    const size_t T1max = entries / L1 + K + 1;
+    const size_t XB = ops->xyzz_bytes;
+
+    uint32_t* counts = c->ws[WS_COUNTS].as<uint32_t>(K + 1);
+    uint32_t* off = c->ws[WS_OFF].as<uint32_t>(K + 1);
+    uint32_t* cursor = c->ws[WS_CURSOR].as<uint32_t>(K + 1);
+    uint32_t* idx = c->ws[WS_IDX].as<uint32_t>(entries);
+    uint32_t* tpb[2] = {c->ws[WS_TPB_A].as<uint32_t>(K + 1), c->ws[WS_TPB_B].as<uint32_t>(K + 1)};
+    uint32_t* tbase[2] = {c->ws[WS_TBASE_A].as<uint32_t>(K + 1), c->ws[WS_TBASE_B].as<uint32_t>(K + 1)};
+    uint32_t* tstart = c->ws[WS_TSTART].as<uint32_t>(T1max);
+    uint32_t* tlen = c->ws[WS_TLEN].as<uint32_t>(T1max);
+    uint32_t* order = c->ws[WS_ORDER].as<uint32_t>(T1max);
+    uint32_t* lenhist = c->ws[WS_LENHIST].as<uint32_t>(1024 + 2);
+    uint32_t* lencur = c->ws[WS_LENCUR].as<uint32_t>(1024 + 2);
+    char* part[2] = {(char*)c->ws[WS_PART_A].get(T1max * XB), (char*)c->ws[WS_PART_B].get((T1max / L2 + K + 1) * XB)};
+    uint32_t* flags = c->ws[WS_FLAGS].as<uint32_t>(4);
+    uint32_t* h_flags = (uint32_t*)c->pin_out.get(64);
+
+    const unsigned grid_stream = (unsigned)c->sm_count * 8;
+    ZKM_CUDA(cudaMemsetAsync(counts, 0, (K + 1) * sizeof(uint32_t), s));
+    ZKM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), s));
+    ZKM_LAUNCH(k_msm_digits<0>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, counts,
+               (uint32_t*)nullptr, flags);
+    exclusive_scan(c, counts, off, K + 1, s);
+    ZKM_CUDA(cudaMemcpyAsync(cursor, off, K * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, cursor, idx,
+               flags);
+
+    // level-1 task list
+    const unsigned kblocks = (K + 1 + 255) / 256;
+    ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, counts, K, L1, tpb[0], flags);
+    exclusive_scan(c, tpb[0], tbase[0], K + 1, s);
+    ZKM_CUDA(cudaMemcpyAsync(h_flags, flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ZKM_CUDA(cudaStreamSynchronize(s));  // the one host sync: largest bucket -> depth of the fold tree
+    if (h_flags[1])
+        ZKM_FAIL(ZKM_ERR_SCALAR_RANGE, "a scalar has bits at or above bit %d (not a canonical Fr)", pl.scalar_bits + 1);
+    const uint32_t maxcnt = h_flags[0];
+
+    auto build_tasks = [&](const uint32_t* tb, const uint32_t* offs, const uint32_t* cnts, uint32_t L) {
+        ZKM_CUDA(cudaMemsetAsync(lenhist, 0, (L + 1) * sizeof(uint32_t), s));
+        ZKM_LAUNCH(k_tasks_emit, grid_stream, 256, (L + 1) * sizeof(uint32_t), s, tb, K, offs, cnts, L, tstart, tlen,
+                   lenhist);
+        ZKM_LAUNCH(k_len_offsets, 1, 32, 0, s, lenhist, L, lencur);
+        ZKM_LAUNCH(k_tasks_order, grid_stream, 256, 0, s, tlen, tb, K, lencur, order);
+    };
+    // 256 threads, one CTA per SM (the accumulators are register-bound), persistent over the task list
+    const unsigned grid_acc = (unsigned)c->sm_count;
+    build_tasks(tbase[0], off, counts, L1);
+    ops->accum_affine(grid_acc, s, d_bases, idx, TaskList{tstart, tlen, order, tbase[0], K}, part[0]);
+
+    int cur = 0;  // tpb[cur] / tbase[cur] / part[cur] describe the current partial sums
+    uint32_t maxseg = (maxcnt + L1 - 1) / L1;
+    while (maxseg > 1) {
+        const int nxt = cur ^ 1;
+        ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, tpb[cur], K, L2, tpb[nxt], (uint32_t*)nullptr);
+        exclusive_scan(c, tpb[nxt], tbase[nxt], K + 1, s);
+        build_tasks(tbase[nxt], tbase[cur], tpb[cur], L2);
+        ops->accum_xyzz(grid_acc, s, part[cur], TaskList{tstart, tlen, order, tbase[nxt], K}, part[nxt]);
+        cur = nxt;
+        maxseg = (maxseg + L2 - 1) / L2;
+    }
+
+    const uint32_t g = pl.B >= 16 ? 16 : pl.B;
+    void* contrib = c->ws[WS_CONTRIB].get((size_t)pl.W * (pl.B / g) * XB);
+    void* wsum = c->ws[WS_WSUM].get((size_t)pl.W * XB);
+    ops->reduce(s, part[cur], tbase[cur], tpb[cur], pl, contrib, wsum, d_out);
+}
+
+void points_sum_run(Context* c, int curve, int group, const uint64_t* d_points, size_t m, uint64_t* d_out,
+                    cudaStream_t s) {
+    (void)c;
+    curve_ops(curve, group)->points_sum(s, d_points, (uint64_t)m, d_out);
+}
+
+void testgen_progression(Context* c, int curve, int group, uint64_t a0, uint64_t d, size_t n, uint64_t* d_out,
+                         cudaStream_t s) {
+    (void)c;
+    curve_ops(curve, group)->gen_progression(s, a0, d, (uint64_t)n, d_out);
+}
+
+}  // namespace zkm

@@ -1,0 +1,48 @@
+// zkm_msm.cuh -- interface between the curve-independent MSM driver (zkm_msm.cu: digit extraction,
+// bucket sort, task lists) and the per-curve translation units (zkm_msm_g{1,2}_{bls,bn}.cu: bucket
+// accumulation and window reduction, instantiated from zkm_msm_curve.cuh).  Splitting them keeps
+// every ptxas job small enough to build in parallel.
+#pragma once
+#include "zkm_common.cuh"
+
+namespace zkm {
+
+struct MsmPlan {
+    int c;         // window bits
+    int W;         // windows = ceil((scalar_bits + 1) / c)
+    uint32_t B;    // buckets per window = 2^(c-1)  (signed digits: |d| in 1..B)
+    uint32_t K;    // W * B
+    int scalar_bits;
+};
+
+// Task list of one fold level: task t sums entries [tstart[t], tstart[t] + tlen[t]); threads walk
+// `order` (tasks sorted by decreasing length) so that the lanes of a warp run equally long loops.
+struct TaskList {
+    const uint32_t* tstart;
+    const uint32_t* tlen;
+    const uint32_t* order;
+    const uint32_t* tbase;  // tbase[K] = number of tasks (device-resident, never read by the host)
+    uint32_t K;
+};
+
+struct CurveOps {
+    int curve, group, scalar_bits;
+    size_t xyzz_bytes;
+    // K4: out[task] = sum of the (sign-adjusted) affine bases named by idx[...]
+    void (*accum_affine)(unsigned grid, cudaStream_t s, const void* bases, const uint32_t* idx, TaskList tl, void* out);
+    // fold level: out[task] = sum of XYZZ items
+    void (*accum_xyzz)(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out);
+    // K5: bucket sums (cnt[k] in {0,1}, item at off[k]) -> affine result record at d_out
+    void (*reduce)(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl, void* contrib,
+                   void* wsum, uint64_t* d_out);
+    void (*write_identity)(cudaStream_t s, uint64_t* d_out);
+    void (*points_sum)(cudaStream_t s, const uint64_t* d_points, uint64_t m, uint64_t* d_out);
+    void (*gen_progression)(cudaStream_t s, uint64_t a0, uint64_t d, uint64_t n, void* d_out);
+};
+
+const CurveOps* ops_g1_bls();
+const CurveOps* ops_g2_bls();
+const CurveOps* ops_g1_bn();
+const CurveOps* ops_g2_bn();
+
+}  // namespace zkm

@@ -1,0 +1,453 @@
+// zkm_ntt.cuh -- radix-2 NTT of the scalar field Fr on sm_100a.
+//
+// Replaces ark-poly 0.3.0 Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place
+// (src/domain/radix2/{mod,fft}.rs: in_order_fft_in_place = io_helper + derange; ifft =
+// derange + oi_helper + size_inv; src/domain/mod.rs: distribute_powers for the coset variants;
+// pin /root/reference/Cargo.lock:338-339; reached from /root/reference/benches/groth16.rs:115 via
+// ark-groth16's witness_map and from benches/marlin.rs:202,311 via the AHP prover).
+// Outputs are unique field elements, so any correct evaluation order is byte-identical.
+//
+// Design (not a translation of io_helper/oi_helper): the log2(n) decimation-in-frequency stages
+// are grouped into passes of R <= 12 stages.  A pass is the "four-step" split of the remaining
+// sub-transform of size n' = 2^(k - s0):  every tile gathers 2^R elements with stride
+// L = n' / 2^R, runs a 2^R-point DIF NTT on chip (8 elements per thread in registers, 3 stages
+// per round, rounds exchanged through XOR-swizzled shared memory), multiplies output u of the
+// tile by w_{n'}^(lo * u) (one table look-up) and writes it back in place at the bit-reversed
+// slot.  The last pass writes each value straight to its natural-order position (the global
+// bit reversal of `derange` folded into the store), so it is out of place.  Coset scaling
+// (x_j * g^j on the first load; g^-j * n^-1 on the last store) and size_inv are fused in.
+// Twiddles are precomputed tables kept in HBM/L2 and reused by every later call.
+//
+// Cost per element: R/2 butterflies per pass (the last stage of a pass has unit twiddles and
+// skips its multiply) + 1 four-step multiply per non-final pass.  HBM traffic: 64 B per element
+// per pass.  On B200 the kernel is bound by the integer pipe (Montgomery products), not by HBM:
+// see DESIGN.md.
+#pragma once
+#include "zkm_common.cuh"
+
+namespace zkm {
+
+template <class P> struct FrRoots;
+template <> struct FrRoots<Bls12_381_FrP> {
+    static constexpr int TWO_ADICITY = BLS12_381_FR_TWO_ADICITY;
+    static __device__ uint32_t root(int i) { return BLS12_381_FR_ROOT[i]; }
+    static __device__ uint32_t root_inv(int i) { return BLS12_381_FR_ROOT_INV[i]; }
+    static __device__ uint32_t gen(int i) { return BLS12_381_FR_GEN[i]; }
+    static __device__ uint32_t gen_inv(int i) { return BLS12_381_FR_GEN_INV[i]; }
+    static __device__ uint32_t two_inv(int i) { return BLS12_381_FR_TWO_INV[i]; }
+};
+template <> struct FrRoots<Bn254_FrP> {
+    static constexpr int TWO_ADICITY = BN254_FR_TWO_ADICITY;
+    static __device__ uint32_t root(int i) { return BN254_FR_ROOT[i]; }
+    static __device__ uint32_t root_inv(int i) { return BN254_FR_ROOT_INV[i]; }
+    static __device__ uint32_t gen(int i) { return BN254_FR_GEN[i]; }
+    static __device__ uint32_t gen_inv(int i) { return BN254_FR_GEN_INV[i]; }
+    static __device__ uint32_t two_inv(int i) { return BN254_FR_TWO_INV[i]; }
+};
+
+template <class P>
+__device__ Fp<P> fr_const(uint32_t (*f)(int)) {
+    Fp<P> r;
+    for (int i = 0; i < P::N; i++) r.l[i] = f(i);
+    return r;
+}
+
+// w_k = ROOT^(2^(adicity - k))  (or its inverse): generator of the order-2^k subgroup
+template <class P>
+__device__ Fp<P> group_gen(int k, bool inverse) {
+    Fp<P> w = inverse ? fr_const<P>(FrRoots<P>::root_inv) : fr_const<P>(FrRoots<P>::root);
+    for (int i = k; i < FrRoots<P>::TWO_ADICITY; i++) w = fp_sqr(w);
+    return w;
+}
+
+// ---------------------------------------------------------------------------------- table generation
+// out[e] = w_k^e (or w_k^-e), e < 2^(k-1)
+template <class P>
+__global__ void k_gen_twiddles(uint32_t* out, int k, int inverse, uint64_t count) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    Fp<P> w = group_gen<P>(k, inverse != 0);
+    Fp<P> r = fp_pow_u64(w, e);
+    st_fp<P>(out + e * P::N, r);
+}
+
+// coset tables: lo[j] = c * g^(+-j), j < nlo ; hi[j] = g^(+-j*nlo), j < nhi ; c = 1 (forward) or n^-1 (inverse)
+template <class P>
+__global__ void k_gen_coset(uint32_t* lo, uint32_t* hi, uint64_t nlo, uint64_t nhi, int inverse, int k) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlo + nhi) return;
+    Fp<P> g = inverse ? fr_const<P>(FrRoots<P>::gen_inv) : fr_const<P>(FrRoots<P>::gen);
+    if (t < nlo) {
+        Fp<P> r = fp_pow_u64(g, t);
+        if (inverse) {
+            Fp<P> ninv = fp_pow_u64(fr_const<P>(FrRoots<P>::two_inv), (uint64_t)k);
+            r = r * ninv;
+        }
+        st_fp<P>(lo + t * P::N, r);
+    } else {
+        uint64_t j = t - nlo;
+        Fp<P> r = fp_pow_u64(g, j * nlo);
+        st_fp<P>(hi + j * P::N, r);
+    }
+}
+
+// group_gen, group_gen_inv, size_inv, generator, generator_inv
+template <class P>
+__global__ void k_domain_constants(uint32_t* out, int k) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st_fp<P>(out + 0 * P::N, group_gen<P>(k, false));
+    st_fp<P>(out + 1 * P::N, group_gen<P>(k, true));
+    st_fp<P>(out + 2 * P::N, fp_pow_u64(fr_const<P>(FrRoots<P>::two_inv), (uint64_t)k));
+    st_fp<P>(out + 3 * P::N, fr_const<P>(FrRoots<P>::gen));
+    st_fp<P>(out + 4 * P::N, fr_const<P>(FrRoots<P>::gen_inv));
+}
+
+// ---------------------------------------------------------------------------------- the pass kernel
+struct NttPassArgs {
+    const uint32_t* in;
+    uint32_t* out;
+    const uint32_t* tw_tile;   // w_{2^R}^e, e < 2^(R-1)
+    const uint32_t* tw_four;   // w_{n'}^e, e < n'/2 (non-final passes)
+    const uint32_t* coset_lo;  // fused coset / size_inv scaling (first or last pass), may be null
+    const uint32_t* coset_hi;
+    const uint32_t* size_inv;  // n^-1 (non-coset inverse, last pass)
+    int k;                     // log2 n
+    int s0;                    // stages already done
+    int first, last;           // pass position
+    int scale_in;              // multiply inputs by coset table (forward coset, first pass)
+    int scale_out;             // 1: multiply outputs by coset table ; 2: by size_inv (last pass)
+    int coset_lo_bits;
+};
+
+template <int R>
+struct NttCfg {
+    static constexpr int TPT = 1 << (R - 3);               // threads per tile
+    static constexpr int NT = TPT > 128 ? TPT : 128;       // threads per CTA
+    static constexpr int TILES = NT / TPT;                 // tiles per CTA iteration
+    static constexpr int SMEM = NT * 8 * 32;               // bytes
+    static constexpr int NR = (R + 2) / 3;                 // register rounds
+};
+
+__device__ __forceinline__ uint32_t ntt_slot(uint32_t tau, uint32_t q, int pl) {
+    return ((tau >> pl) << (pl + 3)) | (q << pl) | (tau & ((1u << pl) - 1u));
+}
+__device__ __forceinline__ uint32_t ntt_phys(uint32_t slot) { return slot ^ ((slot >> 3) & 7u); }
+
+// one DIF stage on q-bit BETA of the 8 register-resident elements
+template <class P, int R, int BETA>
+__device__ __forceinline__ void ntt_stage(Fp<P> (&x)[8], uint32_t tau, int pl, const uint32_t* tw_tile) {
+    const int g = pl + BETA;   // bit position of the butterfly distance inside the tile
+    const int t = R - 1 - g;   // DIF stage index
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (q & (1 << BETA)) continue;
+        const int qb = q | (1 << BETA);
+        Fp<P> lo = x[q], hi = x[qb];
+        x[q] = fp_add(lo, hi);
+        Fp<P> d = fp_sub(lo, hi);
+        if (g == 0) {
+            x[qb] = d;  // w^0
+        } else {
+            uint32_t slot = ntt_slot(tau, q, pl);
+            uint32_t j = slot & ((1u << g) - 1u);
+            Fp<P> w = ld_fp<P>(tw_tile + ((size_t)j << t) * P::N);
+            x[qb] = fp_mul(d, w);
+        }
+    }
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> coset_factor(const NttPassArgs& a, uint64_t idx) {
+    Fp<P> lo = ld_fp<P>(a.coset_lo + (idx & ((1ull << a.coset_lo_bits) - 1ull)) * P::N);
+    Fp<P> hi = ld_fp<P>(a.coset_hi + (idx >> a.coset_lo_bits) * P::N);
+    return fp_mul(lo, hi);
+}
+
+template <class P, int R>
+__global__ void __launch_bounds__(NttCfg<R>::NT) k_ntt_pass(const NttPassArgs a) {
+    typedef NttCfg<R> C;
+    extern __shared__ uint4 ntt_smem[];
+    const uint32_t tl = threadIdx.x / C::TPT;
+    const uint32_t tau = threadIdx.x % C::TPT;
+    uint4* sm0 = ntt_smem + (size_t)tl * (2u << R);
+    uint4* sm1 = sm0 + (1u << R);
+
+    const int kk = a.k - a.s0;          // log2 n'
+    const int logL = kk - R;            // log2 stride
+    const uint64_t num_tiles = 1ull << (a.k - R);
+    const uint64_t lmask = (1ull << logL) - 1ull;
+
+    for (uint64_t base = (uint64_t)blockIdx.x * C::TILES; base < num_tiles; base += (uint64_t)gridDim.x * C::TILES) {
+        const uint64_t tile = base + tl;
+        const bool active = tile < num_tiles;
+        const uint64_t lo_idx = tile & lmask;
+        const uint64_t hi_idx = tile >> logL;
+        const uint64_t gbase = (hi_idx << kk) + lo_idx;
+        Fp<P> x[8];
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                uint64_t gi = gbase + ((uint64_t)ntt_slot(tau, q, R - 3) << logL);
+                x[q] = ld_fp_plain<P>(a.in + gi * P::N);
+                if (a.scale_in) x[q] = fp_mul(x[q], coset_factor<P>(a, gi));
+            }
+        }
+#pragma unroll 1
+        for (int r = 0; r < C::NR; r++) {
+            const int rem = R - 3 * r;
+            const int ns = rem >= 3 ? 3 : rem;
+            const int pl = rem >= 3 ? rem - 3 : 0;
+            if (r > 0) {
+                const int plp = R - 3 * r;  // previous round's pl (>= 0)
+                __syncthreads();
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        uint32_t ph = ntt_phys(ntt_slot(tau, q, plp));
+                        sm0[ph] = make_uint4(x[q].l[0], x[q].l[1], x[q].l[2], x[q].l[3]);
+                        sm1[ph] = make_uint4(x[q].l[4], x[q].l[5], x[q].l[6], x[q].l[7]);
+                    }
+                }
+                __syncthreads();
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        uint32_t ph = ntt_phys(ntt_slot(tau, q, pl));
+                        uint4 v0 = sm0[ph], v1 = sm1[ph];
+                        x[q].l[0] = v0.x; x[q].l[1] = v0.y; x[q].l[2] = v0.z; x[q].l[3] = v0.w;
+                        x[q].l[4] = v1.x; x[q].l[5] = v1.y; x[q].l[6] = v1.z; x[q].l[7] = v1.w;
+                    }
+                }
+            }
+            if (active) {
+                if (ns == 3) ntt_stage<P, R, 2>(x, tau, pl, a.tw_tile);
+                if (ns >= 2) ntt_stage<P, R, 1>(x, tau, pl, a.tw_tile);
+                ntt_stage<P, R, 0>(x, tau, pl, a.tw_tile);
+            }
+        }
+        if (active) {
+            // the thread now holds slots j = 8 tau + q, i.e. outputs u = bitrev_R(j)
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t j = (tau << 3) | q;
+                const uint32_t u = __brev(j) >> (32 - R);
+                if (!a.last) {
+                    // four-step twiddle w_{n'}^(lo * u), then in place at the bit-reversed slot
+                    uint64_t e = lo_idx * (uint64_t)u;
+                    const uint64_t half = 1ull << (kk - 1);
+                    bool negate = e >= half;
+                    if (negate) e -= half;
+                    Fp<P> w = ld_fp<P>(a.tw_four + e * P::N);
+                    Fp<P> v = fp_mul(x[q], w);
+                    if (negate) v = fp_neg(v);
+                    st_fp<P>(a.out + (gbase + ((uint64_t)j << logL)) * P::N, v);
+                } else {
+                    // natural-order position: u * 2^(k-R) + bitrev_{k-R}(hi)
+                    const int hb = a.k - R;
+                    uint64_t hrev = hb ? (uint64_t)(__brevll(hi_idx) >> (64 - hb)) : 0ull;
+                    uint64_t K = ((uint64_t)u << hb) | hrev;
+                    Fp<P> v = x[q];
+                    if (a.scale_out == 1) {
+                        v = fp_mul(v, coset_factor<P>(a, K));
+                    } else if (a.scale_out == 2) {
+                        v = fp_mul(v, ld_fp<P>(a.size_inv));
+                    }
+                    st_fp<P>(a.out + K * P::N, v);
+                }
+            }
+        }
+    }
+}
+
+// n <= 4: direct evaluation of the definition by one thread (k = 0, 1, 2)
+template <class P>
+__global__ void k_ntt_tiny(const uint32_t* in, uint32_t* out, int k, int inverse, int coset) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = 1 << k;
+    Fp<P> x[4], y[4];
+    Fp<P> g = inverse ? fr_const<P>(FrRoots<P>::gen_inv) : fr_const<P>(FrRoots<P>::gen);
+    for (int i = 0; i < n; i++) {
+        x[i] = ld_fp_plain<P>(in + i * P::N);
+        if (coset && !inverse) x[i] = x[i] * fp_pow_u64(g, (uint64_t)i);
+    }
+    Fp<P> w = group_gen<P>(k, inverse != 0);
+    Fp<P> ninv = fp_pow_u64(fr_const<P>(FrRoots<P>::two_inv), (uint64_t)k);
+    for (int o = 0; o < n; o++) {
+        Fp<P> acc = Fp<P>::zero();
+        for (int i = 0; i < n; i++) acc = acc + x[i] * fp_pow_u64(w, (uint64_t)((i * o) % n));
+        if (inverse) {
+            acc = acc * ninv;
+            if (coset) acc = acc * fp_pow_u64(g, (uint64_t)o);
+        }
+        y[o] = acc;
+    }
+    for (int i = 0; i < n; i++) st_fp<P>(out + i * P::N, y[i]);
+}
+
+// ---------------------------------------------------------------------------------- host side
+enum TableKind : uint64_t { TW = 1, COSET_LO = 2, COSET_HI = 3, DOMAIN = 4 };
+static uint64_t table_key(uint64_t kind, int curve, int k, int inverse) {
+    return (kind << 32) | ((uint64_t)curve << 16) | ((uint64_t)inverse << 8) | (uint64_t)k;
+}
+
+template <class P>
+static const uint32_t* get_twiddles(Context* c, int curve, int k, int inverse, cudaStream_t s) {
+    if (k < 1) k = 1;
+    uint64_t key = table_key(TW, curve, k, inverse);
+    auto it = c->twiddles.find(key);
+    if (it != c->twiddles.end()) return (const uint32_t*)it->second;
+    uint64_t count = 1ull << (k - 1);
+    void* p = nullptr;
+    ZKM_CUDA(cudaMalloc(&p, count * P::N * 4));
+    c->twiddles[key] = p;
+    unsigned blocks = (unsigned)((count + 255) / 256);
+    ZKM_LAUNCH(k_gen_twiddles<P>, blocks, 256, 0, s, (uint32_t*)p, k, inverse, count);
+    return (const uint32_t*)p;
+}
+
+template <class P>
+static void get_coset(Context* c, int curve, int k, int inverse, cudaStream_t s, const uint32_t** lo,
+                      const uint32_t** hi, int* lo_bits) {
+    int lb = k < 12 ? k : 12;
+    *lo_bits = lb;
+    uint64_t nlo = 1ull << lb, nhi = 1ull << (k - lb);
+    uint64_t klo = table_key(COSET_LO, curve, k, inverse), khi = table_key(COSET_HI, curve, k, inverse);
+    auto it = c->twiddles.find(klo);
+    if (it != c->twiddles.end()) {
+        *lo = (const uint32_t*)it->second;
+        *hi = (const uint32_t*)c->twiddles[khi];
+        return;
+    }
+    void *pl = nullptr, *ph = nullptr;
+    ZKM_CUDA(cudaMalloc(&pl, nlo * P::N * 4));
+    c->twiddles[klo] = pl;
+    ZKM_CUDA(cudaMalloc(&ph, nhi * P::N * 4));
+    c->twiddles[khi] = ph;
+    unsigned blocks = (unsigned)((nlo + nhi + 255) / 256);
+    ZKM_LAUNCH(k_gen_coset<P>, blocks, 256, 0, s, (uint32_t*)pl, (uint32_t*)ph, nlo, nhi, inverse, k);
+    *lo = (const uint32_t*)pl;
+    *hi = (const uint32_t*)ph;
+}
+
+template <class P, int R>
+static void launch_pass(Context* c, const NttPassArgs& a, cudaStream_t s) {
+    typedef NttCfg<R> C;
+    static bool attr_set = false;
+    if (!attr_set && C::SMEM > 48 * 1024) {
+        ZKM_CUDA(cudaFuncSetAttribute(k_ntt_pass<P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    uint64_t num_tiles = 1ull << (a.k - R);
+    uint64_t ctas = (num_tiles + C::TILES - 1) / C::TILES;
+    // persistent grid: a multiple of the SM count, exactly as many CTAs per SM as are co-resident
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        ZKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ntt_pass<P, R>, C::NT, C::SMEM));
+        if (per_sm < 1) per_sm = 1;
+    }
+    uint64_t cap = (uint64_t)c->sm_count * per_sm;
+    unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
+    ZKM_LAUNCH((k_ntt_pass<P, R>), grid, C::NT, C::SMEM, s, a);
+}
+
+template <class P>
+static void dispatch_pass(Context* c, int R, const NttPassArgs& a, cudaStream_t s) {
+    switch (R) {
+        case 3: launch_pass<P, 3>(c, a, s); break;
+        case 4: launch_pass<P, 4>(c, a, s); break;
+        case 5: launch_pass<P, 5>(c, a, s); break;
+        case 6: launch_pass<P, 6>(c, a, s); break;
+        case 7: launch_pass<P, 7>(c, a, s); break;
+        case 8: launch_pass<P, 8>(c, a, s); break;
+        case 9: launch_pass<P, 9>(c, a, s); break;
+        case 10: launch_pass<P, 10>(c, a, s); break;
+        case 11: launch_pass<P, 11>(c, a, s); break;
+        case 12: launch_pass<P, 12>(c, a, s); break;
+        default: ZKM_FAIL(ZKM_ERR_ARG, "internal: bad NTT radix log %d", R);
+    }
+}
+
+template <class P>
+static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse,
+                      int coset, cudaStream_t s) {
+    const int k = (int)log_n;
+    if (k > FrRoots<P>::TWO_ADICITY)
+        ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %d exceeds the two-adicity %d of Fr", k, FrRoots<P>::TWO_ADICITY);
+    if (k > 30) ZKM_FAIL(ZKM_ERR_ARG, "log_n %d: domains above 2^30 are not supported by this build", k);
+    const uint32_t* in = (const uint32_t*)d_in;
+    uint32_t* out = (uint32_t*)d_out;
+    if (k <= 2) {
+        ZKM_LAUNCH(k_ntt_tiny<P>, 1, 32, 0, s, in, out, k, inverse, coset);
+        return;
+    }
+    int maxR = c->opt.ntt_max_radix_log;
+    if (maxR < 6) maxR = 6;
+    if (maxR > 12) maxR = 12;
+    int passes = (k + maxR - 1) / maxR;
+    int Rs[16];
+    {   // balanced split, every pass >= 3 stages
+        int base = k / passes, extra = k % passes;
+        for (int i = 0; i < passes; i++) Rs[i] = base + (i < extra ? 1 : 0);
+    }
+    const uint64_t n = 1ull << k;
+    // the last pass is out of place; when the caller wants in == out run it through scratch
+    uint32_t* work = nullptr;       // buffer holding the in-place passes
+    uint32_t* final_dst = out;
+    bool copy_back = false;
+    if (passes == 1) {
+        if (in == out) {
+            work = nullptr;
+            final_dst = (uint32_t*)c->ntt_a.get(n * 32);
+            copy_back = true;
+        }
+    } else {
+        if (in == out) {
+            work = out;  // in-place passes directly on the caller's buffer
+            final_dst = (uint32_t*)c->ntt_a.get(n * 32);
+            copy_back = true;
+        } else {
+            work = (uint32_t*)c->ntt_a.get(n * 32);  // first pass reads `in`, writes scratch
+        }
+    }
+    const uint32_t *clo = nullptr, *chi = nullptr;
+    int clo_bits = 0;
+    if (coset) get_coset<P>(c, curve, k, inverse, s, &clo, &chi, &clo_bits);
+    NttPassArgs a;
+    memset(&a, 0, sizeof(a));
+    if (inverse && !coset) {
+        // size_inv lives in a cached 5-element device table of the domain constants
+        uint64_t key = table_key(DOMAIN, curve, k, 0);
+        auto it = c->twiddles.find(key);
+        void* p;
+        if (it == c->twiddles.end()) {
+            ZKM_CUDA(cudaMalloc(&p, 5 * P::N * 4));
+            c->twiddles[key] = p;
+            ZKM_LAUNCH(k_domain_constants<P>, 1, 32, 0, s, (uint32_t*)p, k);
+        } else {
+            p = it->second;
+        }
+        a.size_inv = (const uint32_t*)p + 2 * P::N;
+    }
+    int s0 = 0;
+    for (int pi = 0; pi < passes; pi++) {
+        const int R = Rs[pi];
+        a.k = k;
+        a.s0 = s0;
+        a.first = pi == 0;
+        a.last = pi == passes - 1;
+        a.in = a.first ? in : work;
+        a.out = a.last ? final_dst : work;
+        a.tw_tile = get_twiddles<P>(c, curve, R, inverse, s);
+        a.tw_four = a.last ? nullptr : get_twiddles<P>(c, curve, k - s0, inverse, s);
+        a.coset_lo = clo;
+        a.coset_hi = chi;
+        a.coset_lo_bits = clo_bits;
+        a.scale_in = (a.first && coset && !inverse) ? 1 : 0;
+        a.scale_out = a.last ? (inverse ? (coset ? 1 : 2) : 0) : 0;
+        dispatch_pass<P>(c, R, a, s);
+        s0 += R;
+    }
+    if (copy_back) ZKM_CUDA(cudaMemcpyAsync(out, final_dst, n * 32, cudaMemcpyDeviceToDevice, s));
+}
+
+}  // namespace zkm

@@ -1,0 +1,35 @@
+// zkm_ntt_bls.cu -- NTT kernels instantiated for BLS12-381 Fr, plus the curve dispatch.
+#include "zkm_ntt.cuh"
+
+namespace zkm {
+
+void ntt_run_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset, cudaStream_t s);
+void ntt_domain_constants_bn(Context* c, uint32_t* d, int log_n);
+
+void ntt_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
+             cudaStream_t stream) {
+    if (curve == ZKM_CURVE_BLS12_381) ntt_run_t<Bls12_381_FrP>(c, curve, d_in, d_out, log_n, inverse, coset, stream);
+    else if (curve == ZKM_CURVE_BN254) ntt_run_bn(c, d_in, d_out, log_n, inverse, coset, stream);
+    else ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+}
+
+void ntt_domain_constants(int curve, uint32_t log_n, uint64_t* out5x4_host) {
+    Context* c = ctx();
+    if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+    int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
+    if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
+    uint32_t* d = (uint32_t*)c->io_out.get(5 * 32);
+    if (curve == ZKM_CURVE_BLS12_381) ZKM_LAUNCH(k_domain_constants<Bls12_381_FrP>, 1, 32, 0, c->stream, d, (int)log_n);
+    else ntt_domain_constants_bn(c, d, (int)log_n);
+    ZKM_CUDA(cudaMemcpyAsync(out5x4_host, d, 5 * 32, cudaMemcpyDeviceToHost, c->stream));
+    ZKM_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void ntt_release(Context* c) {
+    for (auto& kv : c->twiddles) cudaFree(kv.second);
+    c->twiddles.clear();
+    c->ntt_a.release();
+    c->ntt_b.release();
+}
+
+}  // namespace zkm

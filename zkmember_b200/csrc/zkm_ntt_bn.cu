@@ -1,0 +1,13 @@
+// zkm_ntt_bn.cu -- NTT kernels instantiated for BN254 Fr.
+#include "zkm_ntt.cuh"
+
+namespace zkm {
+
+void ntt_run_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset, cudaStream_t s) {
+    ntt_run_t<Bn254_FrP>(c, ZKM_CURVE_BN254, d_in, d_out, log_n, inverse, coset, s);
+}
+void ntt_domain_constants_bn(Context* c, uint32_t* d, int log_n) {
+    ZKM_LAUNCH(k_domain_constants<Bn254_FrP>, 1, 32, 0, c->stream, d, log_n);
+}
+
+}  // namespace zkm
