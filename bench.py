@@ -1,0 +1,388 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: "G1 MSM 2^24 ms; NTT 2^24 ms").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+
+One step = one 2^24-point BLS12-381 G1 MSM (BASELINE.json configs[1]: the standalone G1 MSM
+sweep; 2^24 is the size the metric is quoted on).  With N GPUs the 2^24 (base, scalar) pairs are
+range-sharded N ways (strong scaling): every rank runs the full pipeline on its slice, the N
+partial points are all-gathered over NCCL/NVLink and summed on every rank.  `value` is the device
+time of a step with scalars and bases resident in HBM; `e2e` is the same step through the host
+C-ABI call (`zkm_msm_registered`: scalars copied from pinned host memory, result read back; the
+bases are the proving key, registered once -- /root/reference/benches/groth16.rs:107-115 reuses
+`pk` across proofs).  The same run also reports the 2^24 Fr NTT (`ntt`), the stage breakdown of
+the MSM, the roofline of the dominant kernel (bucket accumulation, integer pipe) and the CPU
+baseline: the arkworks-0.3.0 algorithm restated in C++ (oracle/cpp), timed on this box's cores.
+
+`--impl reference` times that CPU restatement (arkworks itself cannot be built: no Rust toolchain,
+crates not vendored) with all host threads on a bounded sample and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = int(os.environ.get("ZKM_BENCH_LOG_N", "24"))
+CURVE_NAME = os.environ.get("ZKM_BENCH_CURVE", "bls12_381")
+CURVE_ID = {"bls12_381": 0, "bn254": 1}[CURVE_NAME]
+L64 = {0: 6, 1: 4}[CURVE_ID]
+MADS_PER_MODMUL = {0: 300, 1: 136}[CURVE_ID]      # 2 n^2 + n wide MADs, n = 12 / 8 32-bit limbs
+ALGO_MODMULS_PER_POINT = 160                       # ceil(255/16) windows x 10 products (XYZZ mixed add), SURVEY 8d
+METRIC = "G1 MSM 2^%d ms (%s)" % (LOG_N, "BLS12-381" if CURVE_ID == 0 else "BN254")
+# Integer-pipe peak: dependent IMAD.WIDE Montgomery chains measured on this pool's B200 by
+# tools/microbench/imad_peak.cu (profiles/imad_peak_r1.jsonl, modmul_fq384 @ 32 warps/SM).
+IMAD_PEAK_GMADS = 9057.7
+CPU_SAMPLE_LOG_N = int(os.environ.get("ZKM_BENCH_CPU_LOG_N", "21"))
+
+
+def read_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_run(steps: int, warmup: int, sample_log_n: int):
+    """The arkworks-0.3.0 MSM algorithm (C++ restatement, oracle/cpp) on the host cores."""
+    import numpy as np
+    from oracle import capi
+    n = 1 << sample_log_n
+    bases = capi.progression(CURVE_ID, 1, 0x1234567, 0x89ABCDE, n)
+    scal = capi.random_scalars(CURVE_ID, n, seed=0x5EED0000 + sample_log_n)
+    cores = capi.lib().orc_num_threads()
+    c_bits = capi.msm_window_bits(n)
+    bits = 255 if CURVE_ID == 0 else 254
+    windows = (bits + c_bits - 1) // c_bits      # window_starts = 0, c, 2c, ... < MODULUS_BITS
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        capi.msm(CURVE_ID, 1, bases, scal)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    scale = (1 << LOG_N) / n
+    return {
+        "value": ms * scale, "unit": "ms", "cores": int(min(cores, windows)), "kind": "port",
+        "sample": "2^%d-point MSM (1/%d of the workload) timed %.1f ms/step with %d OpenMP threads available; arkworks "
+                  "runs one task per window (%d windows at c=%d), value scaled linearly to 2^%d"
+                  % (sample_log_n, int(scale), ms, cores, windows, c_bits, LOG_N),
+        "sample_ms": ms, "host_threads": int(cores),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, args.steps)
+    warmup = min(args.warmup, 1)
+    base = cpu_baseline_run(steps, warmup, CPU_SAMPLE_LOG_N)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "ms", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": base["value"], "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32-limb Montgomery integers", "data": "synthetic",
+        "config": {"workload": "G1 MSM, %s, 2^%d points, uniform scalars; CPU: arkworks-0.3.0 algorithm restated in C++ "
+                               "(oracle/cpp), not the Rust binary" % (CURVE_NAME, LOG_N)},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--skip-ntt", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import zkmember_b200 as zkm
+    from zkmember_b200 import _lib
+    zkm.init(local_rank)
+    L = _lib.lib()
+    # a dedicated (non-default) stream: the library launches on exactly this stream, so the
+    # torch.cuda.Event pairs below bracket its kernels (handle 0 would mean "library's own stream")
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    sp = ctypes.c_void_p(stream)
+
+    n_total = 1 << LOG_N
+    n_local = n_total // world
+    lo = rank * n_local
+    W2 = 2 * L64
+    REC = W2 + 1
+
+    # ---- synthetic inputs: bases with known discrete logs generated on the device,
+    # uniform canonical scalars generated on the host (numpy PCG64, rejection-sampled below r)
+    a0, dstep = 0x1234567, 0x89ABCDE
+    d_bases = torch.empty((n_local, W2), dtype=torch.int64, device=dev)
+    _lib.check(L.zkm_testgen_progression_device(CURVE_ID, 1, a0 + lo * dstep, dstep, n_local,
+                                                ctypes.c_void_p(d_bases.data_ptr()), sp))
+    torch.cuda.synchronize()
+    reg = zkm.RegisteredBases.from_device(CURVE_ID, 1, d_bases.data_ptr(), n_local)
+    del d_bases
+    from oracle import capi  # input generator + checker only
+    h_scal = torch.from_numpy(capi.random_scalars(CURVE_ID, n_local, seed=0x5EED0000 + LOG_N + 1000 * rank)
+                              .view(np.int64)).pin_memory()
+    d_scal = h_scal.to(dev)
+    d_rec = torch.zeros(REC, dtype=torch.int64, device=dev)
+    d_all = torch.zeros((world, REC), dtype=torch.int64, device=dev)
+    d_final = torch.zeros(REC, dtype=torch.int64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        reg.msm_device(d_scal.data_ptr(), n_local, d_rec.data_ptr(), stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all.view(-1), d_rec)
+            _lib.check(L.zkm_points_sum_device(CURVE_ID, 1, ctypes.c_void_p(d_all.data_ptr()), world,
+                                               ctypes.c_void_p(d_final.data_ptr()), sp))
+
+    h_out = np.zeros(W2, dtype=np.uint64)
+    h_inf = np.zeros(1, dtype=np.uint8)
+    h_rec = torch.zeros(REC, dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        """Host buffers in, host result out, through the C ABI."""
+        if world == 1:
+            _lib.check(L.zkm_msm_registered(reg.handle, 0, ctypes.c_void_p(h_scal.data_ptr()), n_local,
+                                            ctypes.c_void_p(h_out.ctypes.data), ctypes.c_void_p(h_inf.ctypes.data)))
+        else:
+            d_s = h_scal.to(dev, non_blocking=True)
+            reg.msm_device(d_s.data_ptr(), n_local, d_rec.data_ptr(), stream=stream)
+            dist.all_gather_into_tensor(d_all.view(-1), d_rec)
+            _lib.check(L.zkm_points_sum_device(CURVE_ID, 1, ctypes.c_void_p(d_all.data_ptr()), world,
+                                               ctypes.c_void_p(d_final.data_ptr()), sp))
+            h_rec.copy_(d_final, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3 / steps
+        ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    # ---- headline: device-resident MSM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    _lib.launch_count(reset=True)
+    if sampler:
+        sampler.start()
+    ms_dev, _ = timed(step_device, args.steps, 0)
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count()
+
+    # ---- correctness of what was timed: known-discrete-log identity (exact big-int check on rank 0)
+    final = (d_final if world > 1 else d_rec).cpu().numpy().view(np.uint64)
+    ok = None
+    if rank == 0 and world == 1:
+        from oracle.py import exact
+        from oracle.py.params import CURVES_BY_ID
+        curve = CURVES_BY_ID[CURVE_ID]
+        s = h_scal.numpy().view(np.uint64).astype(object)
+        sv = s[:, 0] + (s[:, 1] << 64) + (s[:, 2] << 128) + (s[:, 3] << 192)
+        k = int(np.sum(sv * (a0 + np.arange(n_local, dtype=object) * dstep)) % curve.fr.modulus)
+        G = exact.Group(curve, 1)
+        b, f = exact.point_to_bytes(curve, 1, G.mul(G.gen, k))
+        ok = bool(final[W2] == f and final[:W2].tobytes() == b)
+
+    # ---- stage breakdown + roofline of the dominant kernel (rank 0's slice)
+    zkm.set_option("profile", 1)
+    stages = np.zeros(5, dtype=np.float64)
+    acc = np.zeros(5, dtype=np.float64)
+    for _ in range(args.steps):
+        reg.msm_device(d_scal.data_ptr(), n_local, d_rec.data_ptr(), stream=stream)
+        _lib.check(L.zkm_profile_last_msm(ctypes.c_void_p(stages.ctypes.data)))
+        acc += stages
+    zkm.set_option("profile", 0)
+    acc /= args.steps
+    accum_ms = float(acc[2])
+    c_bits = zkm.msm_window_bits(CURVE_ID, 1, n_local)
+    bits = 255 if CURVE_ID == 0 else 254
+    windows = (bits + 1 + c_bits - 1) // c_bits    # signed digits: one spare bit for the carry
+    algo_mads = ALGO_MODMULS_PER_POINT * n_local * MADS_PER_MODMUL
+    actual_mads = windows * 10 * n_local * MADS_PER_MODMUL
+    achieved = algo_mads / (accum_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if tj.get("workload") == "%s_g1_msm_2p%d" % (CURVE_NAME, LOG_N) and world == 1:
+            traffic = tj.get("k_accum_affine_dram_bytes")
+    except Exception:
+        pass
+    roofline = {
+        "kernel": "k_accum_affine (bucket accumulation, XYZZ += affine)", "bound": "int_pipe",
+        "achieved": achieved, "peak": IMAD_PEAK_GMADS, "unit": "GMAD/s", "frac": achieved / IMAD_PEAK_GMADS,
+        "traffic": traffic, "kernel_ms": accum_ms,
+        "algorithmic": "160 Fq products/point (16 windows x 10, SURVEY 8d) x %d wide MADs x %d points"
+                       % (MADS_PER_MODMUL, n_local),
+        "executed_frac": (actual_mads / (accum_ms * 1e-3) / 1e9) / IMAD_PEAK_GMADS,
+        "executed": "%d windows of %d bits x 10 products" % (windows, c_bits),
+        "peak_source": "measured: dependent IMAD.WIDE Montgomery chains, profiles/imad_peak_r1.jsonl (this pool's B200)",
+    }
+
+    # ---- end to end through the host API
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps, 2)
+    e2e = {"value": wall_e2e, "unit": "ms", "h2d_bytes_per_step": int(n_local * 32 * world),
+           "d2h_bytes_per_step": int(REC * 8), "device_ms": ms_e2e,
+           "note": "zkm_msm_registered: scalars from pinned host memory each step, affine result read back; bases "
+                   "(the proving key) registered once; wall clock, max over ranks"}
+
+    # ---- secondary headline: 2^24 Fr NTT (independent transform per GPU)
+    ntt = None
+    if not args.skip_ntt:
+        n_ntt = 1 << LOG_N
+        x = torch.from_numpy(capi.random_field_elements(CURVE_ID, n_ntt, seed=0x5EED1000 + LOG_N).view(np.int64)).to(dev)
+        y = torch.empty_like(x)
+        def step_ntt():
+            _lib.check(L.zkm_ntt_device(CURVE_ID, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), LOG_N,
+                                        0, 0, sp))
+        ms_ntt, _ = timed(step_ntt, max(args.steps, 5), 3)
+        peaks = read_peaks()
+        hbm = peaks["hbm_gbs"] if peaks and "hbm_gbs" in peaks else 6650.0
+        gbs = 64.0 * n_ntt / (ms_ntt * 1e-3) / 1e9
+        ntt = {"metric": "Fr NTT 2^%d ms (%s)" % (LOG_N, CURVE_NAME), "ms": ms_ntt,
+               "ntts_per_s_all_gpus": world * 1e3 / ms_ntt,
+               "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                            "algorithmic": "64 B/element (read once + write once)", "traffic": None},
+               "note": "device-resident, out of place; integer-pipe bound on B200, see DESIGN.md"}
+        del x, y
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_baseline_run(1, 0, CPU_SAMPLE_LOG_N)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": ms_dev, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32-limb Montgomery integers (381-bit Fq, 255-bit Fr)", "data": "synthetic",
+            "config": {"workload": "G1 MSM, %s, 2^%d points total (range-sharded %d-way), uniform canonical scalars, "
+                                   "bases (a0+i*d)*G" % (CURVE_NAME, LOG_N, world),
+                       "window_bits": c_bits, "windows": windows, "l2": "inputs larger than L2 (scalars %d MiB + bases "
+                       "%d MiB per GPU)" % (n_local * 32 >> 20, n_local * W2 * 8 >> 20),
+                       "result_check": "known-discrete-log identity, exact big-int" if ok is not None else "n/a (N>1)",
+                       "result_ok": ok},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "msm_stage_ms": {"sort": acc[0], "tasks": acc[1], "accumulate": acc[2], "fold": acc[3], "reduce": acc[4]},
+            "cpu_baseline": cpu, "ntt": ntt,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if (ok is None or ok) else 2
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -114,8 +114,11 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
 
 /* ---- tuning / introspection ------------------------------------------------------------------ */
 /* key: "msm_window_bits" (0 = automatic), "msm_chunk" (points per accumulation task, 0 = auto),
- * "ntt_max_radix_log" (3..12).  Unknown keys fail with ZKM_ERR_ARG. */
+ * "ntt_max_radix_log" (6..12), "profile" (0 | 1).  Unknown keys fail with ZKM_ERR_ARG. */
 int32_t zkm_set_option(const char* key, int64_t value);
+/* With option "profile" = 1: device time (ms, CUDA events on the launching stream) of the five
+ * stages of the last MSM: bucket sort | task lists | bucket accumulation | folds | window reduction. */
+int32_t zkm_profile_last_msm(double* ms_out5);
 /* Kernel launches issued by this library since the last call with reset != 0. */
 uint64_t zkm_launch_count(int32_t reset);
 /* Window bits the automatic choice uses for an n-point MSM (for reports). */

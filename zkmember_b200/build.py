@@ -42,19 +42,34 @@ def _nvcc() -> str:
     return "nvcc"
 
 
-def _headers_digest() -> bytes:
+BASE_HEADERS = ["zkm_common.cuh", "zkm_curve.cuh", "zkm_field.cuh", "zkm_arith.cuh", "zkm_constants.cuh"]
+UNIT_HEADERS = {
+    "zkm_api.cu": [],
+    "zkm_ntt_bls.cu": ["zkm_ntt.cuh"],
+    "zkm_ntt_bn.cu": ["zkm_ntt.cuh"],
+    "zkm_msm.cu": ["zkm_msm.cuh"],
+    "zkm_msm_g1_bls.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh"],
+    "zkm_msm_g2_bls.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh"],
+    "zkm_msm_g1_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh"],
+    "zkm_msm_g2_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh"],
+}
+
+
+def _headers_digest(unit: str) -> bytes:
+    """Hash of exactly the headers `unit` includes (so touching one kernel family does not rebuild all)."""
     h = hashlib.sha256()
-    for d in (CSRC, os.path.join(ROOT, "include")):
-        for name in sorted(os.listdir(d)):
-            if name.endswith((".cuh", ".h")):
-                h.update(name.encode())
-                h.update(open(os.path.join(d, name), "rb").read())
+    paths = [os.path.join(ROOT, "include", "zkm_b200.h")]
+    paths += [os.path.join(CSRC, n) for n in BASE_HEADERS + UNIT_HEADERS[unit]]
+    for path in paths:
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.digest()
 
 
-def _compile(unit: str, hdr: bytes, verbose: bool) -> str:
+def _compile(unit: str, verbose: bool) -> str:
     src = os.path.join(CSRC, unit)
+    hdr = _headers_digest(unit)
     key = hashlib.sha256(hdr + open(src, "rb").read()).hexdigest()[:16]
     obj = os.path.join(OBJ_DIR, unit.replace(".cu", "") + "." + key + ".o")
     if os.path.exists(obj):
@@ -73,10 +88,9 @@ def _compile(unit: str, hdr: bytes, verbose: bool) -> str:
 def build(verbose: bool = True, jobs: int | None = None) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
-    hdr = _headers_digest()
     jobs = jobs or min(len(UNITS), os.cpu_count() or 4)
     with ThreadPoolExecutor(max_workers=jobs) as ex:
-        objs = list(ex.map(lambda u: _compile(u, hdr, verbose), UNITS))
+        objs = list(ex.map(lambda u: _compile(u, verbose), UNITS))
     stamp = hashlib.sha256("".join(objs).encode()).hexdigest()
     stamp_file = LIB + ".stamp"
     if os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:

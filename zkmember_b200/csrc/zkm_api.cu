@@ -152,6 +152,8 @@ void zkm_shutdown(void) {
         if (kv.second.d_inf) cudaFree(kv.second.d_inf);
     }
     c->bases.clear();
+    for (auto& e : c->pev)
+        if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     g_ctx = nullptr;
@@ -320,8 +322,26 @@ int32_t zkm_set_option(const char* key, int64_t value) {
         } else if (!strcmp(key, "ntt_max_radix_log")) {
             if (value < 6 || value > 12) ZKM_FAIL(ZKM_ERR_ARG, "ntt_max_radix_log must be 6..12");
             c->opt.ntt_max_radix_log = (int)value;
+        } else if (!strcmp(key, "profile")) {
+            c->opt.profile = value ? 1 : 0;
         } else {
             ZKM_FAIL(ZKM_ERR_ARG, "unknown option '%s'", key);
+        }
+    });
+}
+
+int32_t zkm_profile_last_msm(double* ms_out5) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (!ms_out5) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->pev_valid) ZKM_FAIL(ZKM_ERR_ARG, "no profiled MSM yet (set option \"profile\" to 1 first)");
+        ZKM_CUDA(cudaSetDevice(c->device));
+        ZKM_CUDA(cudaEventSynchronize(c->pev[5]));
+        for (int i = 0; i < 5; i++) {
+            float ms = 0.f;
+            ZKM_CUDA(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
+            ms_out5[i] = ms;
         }
     });
 }

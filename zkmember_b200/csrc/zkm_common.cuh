@@ -101,6 +101,7 @@ struct Options {
     int msm_window_bits = 0;
     int msm_chunk = 0;
     int ntt_max_radix_log = 10;
+    int profile = 0;  // record CUDA events at the MSM stage boundaries
 };
 
 struct Context {
@@ -119,6 +120,10 @@ struct Context {
     PinnedBuf pin_in, pin_out;
     std::map<uint64_t, BasesReg> bases;
     uint64_t next_handle = 1;
+    // stage timing of the last MSM (opt.profile): events at the boundaries of
+    // sort | task lists | bucket accumulation | fold levels | window reduction
+    cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool pev_valid = false;
 };
 
 Context* ctx();            // throws ZKM_ERR_NOT_INIT when zkm_init has not succeeded

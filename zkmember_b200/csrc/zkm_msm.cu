@@ -248,6 +248,14 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     uint32_t* flags = c->ws[WS_FLAGS].as<uint32_t>(4);
     uint32_t* h_flags = (uint32_t*)c->pin_out.get(64);
 
+    const bool prof = c->opt.profile != 0;
+    auto mark = [&](int i) {
+        if (!prof) return;
+        if (!c->pev[i]) ZKM_CUDA(cudaEventCreate(&c->pev[i]));
+        ZKM_CUDA(cudaEventRecord(c->pev[i], s));
+    };
+    c->pev_valid = false;
+    mark(0);
     const unsigned grid_stream = (unsigned)c->sm_count * 8;
     ZKM_CUDA(cudaMemsetAsync(counts, 0, (K + 1) * sizeof(uint32_t), s));
     ZKM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), s));
@@ -258,6 +266,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, cursor, idx,
                flags);
 
+    mark(1);
     // level-1 task list
     const unsigned kblocks = (K + 1 + 255) / 256;
     ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, counts, K, L1, tpb[0], flags);
@@ -278,8 +287,10 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     // 256 threads, one CTA per SM (the accumulators are register-bound), persistent over the task list
     const unsigned grid_acc = (unsigned)c->sm_count;
     build_tasks(tbase[0], off, counts, L1);
+    mark(2);
     ops->accum_affine(grid_acc, s, d_bases, idx, TaskList{tstart, tlen, order, tbase[0], K}, part[0]);
 
+    mark(3);
     int cur = 0;  // tpb[cur] / tbase[cur] / part[cur] describe the current partial sums
     uint32_t maxseg = (maxcnt + L1 - 1) / L1;
     while (maxseg > 1) {
@@ -292,10 +303,13 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         maxseg = (maxseg + L2 - 1) / L2;
     }
 
+    mark(4);
     const uint32_t g = pl.B >= 16 ? 16 : pl.B;
     void* contrib = c->ws[WS_CONTRIB].get((size_t)pl.W * (pl.B / g) * XB);
     void* wsum = c->ws[WS_WSUM].get((size_t)pl.W * XB);
     ops->reduce(s, part[cur], tbase[cur], tpb[cur], pl, contrib, wsum, d_out);
+    mark(5);
+    c->pev_valid = prof;
 }
 
 void points_sum_run(Context* c, int curve, int group, const uint64_t* d_points, size_t m, uint64_t* d_out,
