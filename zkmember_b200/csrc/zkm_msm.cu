@@ -27,10 +27,13 @@ namespace zkm {
 
 // ---------------------------------------------------------------------------------- K2 / K3 digits
 
-// MODE 0: histogram into counts[K].  MODE 1: scatter (index | sign << 31) at cursor[key]++.
+// MODE 0: histogram into counts[K] (all windows).  MODE 1: scatter (index | sign << 31) at cursor[key]++
+// for window w_only: one launch per window keeps the write set (n x 4 B) inside the 126 MB L2, so the
+// random 4-byte stores merge into full sectors before they reach HBM.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
-                                                    uint64_t n, MsmPlan pl, uint32_t* __restrict__ counts_or_cursor,
+                                                    uint64_t n, MsmPlan pl, int w_only,
+                                                    uint32_t* __restrict__ counts_or_cursor,
                                                     uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         if (inf && inf[i]) continue;
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
             } else {
                 nb = 64;  // flush: the rest of the buffer is zero extension
             }
-            while (nb >= pl.c && w < pl.W) {
+            while (nb >= pl.c && w < pl.W && (MODE == 0 || w <= w_only)) {
                 uint32_t d = ((uint32_t)buf & mask) + carry;
                 buf >>= pl.c;
                 nb -= pl.c;
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                     sign = 1;
                     carry = 1;
                 }
-                if (d != 0) {
+                if (d != 0 && (MODE == 0 || w == w_only)) {
                     uint32_t key = (uint32_t)w * pl.B + (d - 1);
                     if (MODE == 0) {
                         atomicAdd(&counts_or_cursor[key], 1u);
@@ -259,12 +262,13 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     const unsigned grid_stream = (unsigned)c->sm_count * 8;
     ZKM_CUDA(cudaMemsetAsync(counts, 0, (K + 1) * sizeof(uint32_t), s));
     ZKM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), s));
-    ZKM_LAUNCH(k_msm_digits<0>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, counts,
+    ZKM_LAUNCH(k_msm_digits<0>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
                (uint32_t*)nullptr, flags);
     exclusive_scan(c, counts, off, K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(cursor, off, K * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, cursor, idx,
-               flags);
+    for (int w = 0; w < pl.W; w++)
+        ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w, cursor,
+                   idx, flags);
 
     mark(1);
     // level-1 task list
@@ -304,8 +308,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     }
 
     mark(4);
-    const uint32_t g = pl.B >= 16 ? 16 : pl.B;
-    void* contrib = c->ws[WS_CONTRIB].get((size_t)pl.W * (pl.B / g) * XB);
+    void* contrib = c->ws[WS_CONTRIB].get(msm_contrib_records(pl.W, pl.B) * XB);
     void* wsum = c->ws[WS_WSUM].get((size_t)pl.W * XB);
     ops->reduce(s, part[cur], tbase[cur], tpb[cur], pl, contrib, wsum, d_out);
     mark(5);

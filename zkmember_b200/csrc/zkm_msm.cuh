@@ -40,6 +40,14 @@ struct CurveOps {
     void (*gen_progression)(cudaStream_t s, uint64_t a0, uint64_t d, uint64_t n, void* d_out);
 };
 
+// buckets per reduction thread: large enough that the lo * run scalar multiple is a small overhead
+inline uint32_t msm_reduce_group(uint32_t B) { return B >= 4096 ? 64u : (B >= 16 ? 16u : B); }
+// XYZZ records needed by CurveOps::reduce for `contrib`
+inline size_t msm_contrib_records(int W, uint32_t B) {
+    uint32_t per_w = B / msm_reduce_group(B);
+    return (size_t)W * per_w + (size_t)W * ((per_w + 1023) / 1024) + 1;
+}
+
 const CurveOps* ops_g1_bls();
 const CurveOps* ops_g2_bls();
 const CurveOps* ops_g1_bn();

@@ -126,6 +126,18 @@ k_accum_xyzz(const XYZZ<F>* __restrict__ items, const TaskList tl, XYZZ<F>* __re
 }
 
 // ---------------------------------------------------------------------------------- K5 reduction
+// The G1 kernels inline the group law at the few hot call sites of the reduction (registers instead
+// of local memory); G2 keeps the out-of-line copies (four times the code per formula).
+template <class F> struct InlineLaw { static constexpr bool value = sizeof(F) <= 48; };
+template <class F>
+__device__ __forceinline__ void add_sel(XYZZ<F>& p, const XYZZ<F>& q) {
+    if (InlineLaw<F>::value) xyzz_add(p, q); else xyzz_add_ni(p, q);
+}
+template <class F>
+__device__ __forceinline__ void dbl_sel(XYZZ<F>& p) {
+    if (InlineLaw<F>::value) xyzz_dbl(p); else xyzz_dbl_ni(p);
+}
+
 // Thread (w, t) owns buckets b in [t*g, (t+1)*g) of window w:  sum_b (b+1) S_b = acc + lo * run with
 // run = sum S_b, acc = sum (b - lo + 1) S_b (running sums from the top), lo = t*g.
 template <class F>
@@ -142,9 +154,9 @@ k_bucket_reduce(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ 
         const uint32_t k = w * B + b;
         if (cnt[k]) {
             XYZZ<F> S = ld_xyzz(items + off[k]);
-            xyzz_add_ni(run, S);
+            add_sel(run, S);
         }
-        xyzz_add_ni(acc, run);
+        add_sel(acc, run);
     }
     if (lo != 0 && !run.is_identity()) {
         XYZZ<F> r = XYZZ<F>::identity();
@@ -157,15 +169,18 @@ k_bucket_reduce(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ 
     st_xyzz(contrib + gid, acc);
 }
 
+// out[w * nslices + slice] = sum of in[w * per_w + slice * chunk ... + chunk)   (block = 64 threads)
 template <class F>
-__global__ void __launch_bounds__(64) k_window_sum(const XYZZ<F>* __restrict__ contrib, uint32_t per_w,
-                                                   XYZZ<F>* __restrict__ wsum) {
+__global__ void __launch_bounds__(64) k_window_sum(const XYZZ<F>* __restrict__ in, uint32_t per_w, uint32_t chunk,
+                                                   uint32_t nslices, XYZZ<F>* __restrict__ out) {
     __shared__ XYZZ<F> sh[64];
-    const uint32_t w = blockIdx.x;
+    const uint32_t w = blockIdx.x / nslices, slice = blockIdx.x % nslices;
+    const uint32_t begin = slice * chunk;
+    const uint32_t end = begin + chunk < per_w ? begin + chunk : per_w;
     XYZZ<F> acc = XYZZ<F>::identity();
-    for (uint32_t t = threadIdx.x; t < per_w; t += 64) {
-        XYZZ<F> q = ld_xyzz(contrib + (size_t)w * per_w + t);
-        xyzz_add_ni(acc, q);
+    for (uint32_t t = begin + threadIdx.x; t < end; t += 64) {
+        XYZZ<F> q = ld_xyzz(in + (size_t)w * per_w + t);
+        add_sel(acc, q);
     }
     sh[threadIdx.x] = acc;
     __syncthreads();
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(64) k_window_sum(const XYZZ<F>* __restrict__ c
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_xyzz(wsum + w, sh[0]);
+    if (threadIdx.x == 0) st_xyzz(out + blockIdx.x, sh[0]);
 }
 
 // result record: x, y (Montgomery affine), then one u64 flag (1 = point at infinity; x = 0, y = 1 like
@@ -202,7 +217,7 @@ __global__ void k_msm_final(const XYZZ<F>* __restrict__ wsum, int W, int c, uint
     XYZZ<F> total = XYZZ<F>::identity();
     for (int w = W - 1; w >= 0; w--) {
         if (w != W - 1)
-            for (int k = 0; k < c; k++) xyzz_dbl_ni(total);
+            for (int k = 0; k < c; k++) dbl_sel(total);
         XYZZ<F> s = ld_xyzz(wsum + w);
         xyzz_add_ni(total, s);
     }
@@ -271,12 +286,24 @@ struct OpsImpl {
     }
     static void reduce(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl,
                        void* contrib, void* wsum, uint64_t* d_out) {
-        uint32_t g = pl.B >= 16 ? 16 : pl.B;
+        uint32_t g = msm_reduce_group(pl.B);
         uint32_t per_w = pl.B / g;
         unsigned rblocks = ((unsigned)pl.W * per_w + 127) / 128;
         ZKM_LAUNCH(k_bucket_reduce<F>, rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, (uint32_t)pl.W, pl.B, g,
                    (XYZZ<F>*)contrib);
-        ZKM_LAUNCH(k_window_sum<F>, (unsigned)pl.W, 64, 0, s, (const XYZZ<F>*)contrib, per_w, (XYZZ<F>*)wsum);
+        // two-step sum of the per-slice contributions of every window: per_w -> nslices -> 1
+        XYZZ<F>* stage = (XYZZ<F>*)contrib + (size_t)pl.W * per_w;
+        uint32_t nslices = (per_w + 1023) / 1024;
+        if (nslices > 1) {
+            uint32_t chunk = (per_w + nslices - 1) / nslices;
+            ZKM_LAUNCH(k_window_sum<F>, (unsigned)pl.W * nslices, 64, 0, s, (const XYZZ<F>*)contrib, per_w, chunk, nslices,
+                       stage);
+            ZKM_LAUNCH(k_window_sum<F>, (unsigned)pl.W, 64, 0, s, (const XYZZ<F>*)stage, nslices, nslices, 1u,
+                       (XYZZ<F>*)wsum);
+        } else {
+            ZKM_LAUNCH(k_window_sum<F>, (unsigned)pl.W, 64, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u,
+                       (XYZZ<F>*)wsum);
+        }
         ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.W, pl.c, d_out);
     }
     static void write_identity(cudaStream_t s, uint64_t* d_out) { ZKM_LAUNCH(k_write_identity<F>, 1, 32, 0, s, d_out); }
