@@ -88,6 +88,18 @@ int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scala
  * log_n > TWO_ADICITY (32 for BLS12-381 Fr, 28 for BN254 Fr) fails with ZKM_ERR_DOMAIN. */
 int32_t zkm_ntt(int32_t curve, uint64_t* data, uint32_t log_n, int32_t inverse, int32_t coset);
 
+/* Replaces the FFT section of ark_groth16::R1CStoQAP::witness_map (ark-groth16 0.3.0 src/r1cs_to_qap.rs,
+ * reached from /root/reference/benches/groth16.rs:115): given the evaluation vectors a, b, c over the
+ * domain (2^log_n Montgomery elements each, already built and zero-padded by the caller as upstream does),
+ * returns h = coset_ifft((coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / (g^n - 1)) --
+ * seven NTTs and the pointwise step chained in HBM (one upload of a, b, c and one download of h instead
+ * of fourteen PCIe crossings).  HOST pointers; inputs are not modified. */
+int32_t zkm_witness_map(int32_t curve, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,
+                        uint64_t* h_out);
+/* Device-resident form: d_a, d_b, d_c are consumed (overwritten), d_h receives the 2^log_n coefficients. */
+int32_t zkm_witness_map_device(int32_t curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n,
+                               uint64_t* d_h, void* stream);
+
 /* Radix2EvaluationDomain::new: the five domain constants, Montgomery, 4 words each:
  * group_gen, group_gen_inv, size_inv, generator (= GENERATOR), generator_inv. */
 int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5x4);
@@ -114,7 +126,10 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
 
 /* ---- tuning / introspection ------------------------------------------------------------------ */
 /* key: "msm_window_bits" (0 = automatic), "msm_chunk" (points per accumulation task, 0 = auto),
- * "ntt_max_radix_log" (6..12), "profile" (0 | 1).  Unknown keys fail with ZKM_ERR_ARG. */
+ * "ntt_max_radix_log" (6..12), "profile" (0 | 1), "msm_precompute" (0 | 1: bases registered while it is
+ * set also store their window multiples 2^(c w) P -- W times the memory, one-time cost -- so that all
+ * windows of later MSMs share one bucket set and the final doubling chain disappears; meant for proving
+ * keys / SRS that are reused across many proofs).  Unknown keys fail with ZKM_ERR_ARG. */
 int32_t zkm_set_option(const char* key, int64_t value);
 /* With option "profile" = 1: device time (ms, CUDA events on the launching stream) of the five
  * stages of the last MSM: bucket sort | task lists | bucket accumulation | folds | window reduction. */

@@ -55,6 +55,7 @@ def lib():
                                       ctypes.c_size_t, u64p]
         L.orc_field_op.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, u64p]
         L.orc_msm_window_bits.argtypes = [ctypes.c_size_t]
+        L.orc_witness_map.argtypes = [ctypes.c_int, u64p, u64p, u64p, ctypes.c_int, u64p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -100,6 +101,21 @@ def ntt(curve_id: int, data: np.ndarray, inverse: bool = False, coset: bool = Fa
     if rc:
         raise RuntimeError("orc_ntt rc=%d" % rc)
     return x
+
+
+def witness_map(curve_id: int, a: np.ndarray, b: np.ndarray, c: np.ndarray, threads: int = 0) -> np.ndarray:
+    """ark-groth16 0.3.0 R1CStoQAP::witness_map after the matrix-vector products: returns h (n, 4)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    c = np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4)
+    n = len(a)
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n and len(b) == n and len(c) == n
+    h = np.zeros_like(a)
+    rc = lib().orc_witness_map(curve_id, _p64(a), _p64(b), _p64(c), log_n, _p64(h), threads)
+    if rc:
+        raise RuntimeError("orc_witness_map rc=%d" % rc)
+    return h
 
 
 def domain(curve_id: int, log_n: int) -> dict:

@@ -659,6 +659,39 @@ int orc_field_op(int field, int op, const u64* a, const u64* b, u64* out) {
     }
     return -1;
 }
+// ark-groth16 0.3.0 src/r1cs_to_qap.rs R1CStoQAP::witness_map, the part after a, b, c have been
+// evaluated: ifft(a), ifft(b), coset_fft(a), coset_fft(b), ab = a.b, ifft(c), coset_fft(c), ab -= c,
+// ab *= 1 / Z_H(g) with Z_H(g) = g^n - 1, coset_ifft(ab); returns ab (n coefficients) in h.
+int orc_witness_map(int curve, const u64* a, const u64* b, const u64* c, int log_n, u64* h, int threads) {
+#define ORC_WMAP(T, GEN, ADIC)                                                                  \
+    {                                                                                           \
+        typedef Fp<T> F;                                                                        \
+        Domain<F> d;                                                                            \
+        if (!make_domain<T>(d, log_n, GEN, ADIC)) return -2;                                    \
+        if (threads > 0) omp_set_num_threads(threads);                                          \
+        std::vector<F> va(d.n), vb(d.n), vc(d.n);                                               \
+        memcpy(va.data(), a, d.n * sizeof(F));                                                  \
+        memcpy(vb.data(), b, d.n * sizeof(F));                                                  \
+        memcpy(vc.data(), c, d.n * sizeof(F));                                                  \
+        ntt_arkworks(va.data(), d, 1, 0);                                                       \
+        ntt_arkworks(vb.data(), d, 1, 0);                                                       \
+        ntt_arkworks(va.data(), d, 0, 1);                                                       \
+        ntt_arkworks(vb.data(), d, 0, 1);                                                       \
+        for (size_t i = 0; i < d.n; i++) va[i] = va[i] * vb[i];                                 \
+        ntt_arkworks(vc.data(), d, 1, 0);                                                       \
+        ntt_arkworks(vc.data(), d, 0, 1);                                                       \
+        F z = d.generator;                                                                      \
+        for (int i = 0; i < log_n; i++) z = z.sqr();                                            \
+        F zinv = (z - F::one()).inverse();                                                      \
+        for (size_t i = 0; i < d.n; i++) va[i] = (va[i] - vc[i]) * zinv;                        \
+        ntt_arkworks(va.data(), d, 1, 1);                                                       \
+        memcpy(h, va.data(), d.n * sizeof(F));                                                  \
+        return 0;                                                                               \
+    }
+    if (curve == 0) ORC_WMAP(BlsFrTag, 7, 32)
+    if (curve == 1) ORC_WMAP(BnFrTag, 5, 28)
+    return -1;
+}
 int orc_num_threads(void) { return omp_get_max_threads(); }
 int orc_msm_window_bits(size_t n) { return n < 32 ? 3 : (int)ln_without_floats(n) + 2; }
 }

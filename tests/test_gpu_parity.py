@@ -284,3 +284,41 @@ def test_points_sum_device(zkm, curve, g):
         want = G.add(want, P)
     b, f = exact.point_to_bytes(curve, g, want)
     assert out[2 * W] == f and out[:2 * W].tobytes() == b
+
+
+# ------------------------------------------------------------------------------- 8f rows: witness map, precompute
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("log_n", [3, 10, 15])
+def test_witness_map_matches_oracle(zkm, curve, log_n):
+    from zkmember_b200.groth16 import witness_map
+    n = 1 << log_n
+    a = capi.random_field_elements(curve.curve_id, n, seed=1 + log_n)
+    b = capi.random_field_elements(curve.curve_id, n, seed=2 + log_n)
+    c = capi.random_field_elements(curve.curve_id, n, seed=3 + log_n)
+    want = capi.witness_map(curve.curve_id, a, b, c)
+    got = witness_map(a, b, c, curve=curve.name)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("g", [1, 2])
+def test_msm_precomputed_window_multiples(zkm, curve, g):
+    """Registrations with precomputed window multiples give the same point, incl. offsets, infinity, +-P."""
+    n = 3000 if g == 1 else 600
+    bases = capi.progression(curve.curve_id, g, 21, 13, n)
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[[5, 77]] = 1
+    bases[9] = bases[8]
+    zkm.set_option("msm_precompute", 1)
+    try:
+        reg = zkm.RegisteredBases(curve.name, g, bases, inf)
+    finally:
+        zkm.set_option("msm_precompute", 0)
+    try:
+        for kind, off, m in (("uniform", 0, n), ("witness", 0, n), ("uniform", 100, 333), ("small", n - 1, 1), ("uniform", 7, 0)):
+            scal = capi.random_scalars(curve.curve_id, m, seed=off + m + g, kind=kind)
+            want_xy, want_inf = capi.msm(curve.curve_id, g, bases[off:off + m], scal, inf[off:off + m])
+            got = reg.msm(scal, offset=off)
+            _check_point(curve, g, got, want_xy, want_inf)
+    finally:
+        reg.release()

@@ -1,0 +1,105 @@
+#!/usr/bin/env python3
+"""Standalone sweeps (BASELINE.json configs 2 and 3): G1/G2 MSM and Fr NTT over a range of sizes,
+device-resident timings with CUDA events, one JSON line per point.
+
+  python tools/sweep.py msm --curve bls12_381 --group 1 --min 14 --max 24 [--kind uniform|witness]
+  python tools/sweep.py ntt --curve bls12_381 --min 14 --max 26
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import zkmember_b200 as zkm  # noqa: E402
+from zkmember_b200 import _lib  # noqa: E402
+from oracle import capi  # noqa: E402  (input generator only)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("what", choices=["msm", "ntt"])
+ap.add_argument("--curve", default="bls12_381")
+ap.add_argument("--group", type=int, default=1)
+ap.add_argument("--min", type=int, default=14)
+ap.add_argument("--max", type=int, default=24)
+ap.add_argument("--kind", default="uniform")
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle (arkworks algorithm restated) up to 2^20")
+args = ap.parse_args()
+
+cid = {"bls12_381": 0, "bn254": 1}[args.curve]
+zkm.init(0)
+L = _lib.lib()
+dev = torch.device("cuda:0")
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)
+sp = ctypes.c_void_p(st.cuda_stream)
+
+
+def timeit(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+if args.what == "msm":
+    W = (6 if cid == 0 else 4) * args.group
+    nmax = 1 << args.max
+    d_bases = torch.empty((nmax, 2 * W), dtype=torch.int64, device=dev)
+    _lib.check(L.zkm_testgen_progression_device(cid, args.group, 0x1234567, 0x89ABCDE, nmax,
+                                                ctypes.c_void_p(d_bases.data_ptr()), sp))
+    torch.cuda.synchronize()
+    reg = zkm.RegisteredBases.from_device(cid, args.group, d_bases.data_ptr(), nmax)
+    del d_bases
+    d_rec = torch.zeros(2 * W + 1, dtype=torch.int64, device=dev)
+    for lg in range(args.min, args.max + 1):
+        n = 1 << lg
+        h = capi.random_scalars(cid, n, seed=0x5EED0000 + lg, kind=args.kind)
+        d_s = torch.from_numpy(h.view(np.int64)).to(dev)
+        zkm.set_option("profile", 1)
+        med, best = timeit(lambda: reg.msm_device(d_s.data_ptr(), n, d_rec.data_ptr(), stream=st.cuda_stream), args.reps)
+        stages = np.zeros(5)
+        _lib.check(L.zkm_profile_last_msm(ctypes.c_void_p(stages.ctypes.data)))
+        row = {"op": "msm", "curve": args.curve, "group": args.group, "log_n": lg, "kind": args.kind, "ms": med,
+               "ms_best": best, "window_bits": zkm.msm_window_bits(cid, args.group, n),
+               "stage_ms": dict(zip(["sort", "tasks", "accumulate", "fold", "reduce"], [round(float(v), 4) for v in stages]))}
+        if args.cpu and lg <= 20:
+            import time
+            hb = capi.progression(cid, args.group, 0x1234567, 0x89ABCDE, n)
+            t0 = time.perf_counter()
+            capi.msm(cid, args.group, hb, h)
+            row["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+        print(json.dumps(row), flush=True)
+else:
+    for lg in range(args.min, args.max + 1):
+        n = 1 << lg
+        hx = capi.random_field_elements(cid, n, seed=0x5EED1000 + lg)
+        x = torch.from_numpy(hx.view(np.int64)).to(dev)
+        y = torch.empty_like(x)
+        row = {"op": "ntt", "curve": args.curve, "log_n": lg}
+        for name, inv, cos in (("fft", 0, 0), ("ifft", 1, 0), ("coset_fft", 0, 1), ("coset_ifft", 1, 1)):
+            med, best = timeit(lambda: _lib.check(L.zkm_ntt_device(cid, ctypes.c_void_p(x.data_ptr()),
+                                                                   ctypes.c_void_p(y.data_ptr()), lg, inv, cos, sp)), args.reps)
+            row[name + "_ms"] = med
+        row["hbm_frac_fft"] = 64.0 * n / (row["fft_ms"] * 1e-3) / 6539.9e9
+        if args.cpu and lg <= 22:
+            import time
+            t0 = time.perf_counter()
+            capi.ntt(cid, hx)
+            row["cpu_fft_ms"] = (time.perf_counter() - t0) * 1e3
+        print(json.dumps(row), flush=True)
+        del x, y

@@ -52,14 +52,14 @@ static void h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 }
 
 static void msm_host(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* scalars,
-                     size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+                     size_t n, uint64_t* out_xy, uint8_t* out_inf, const BasesReg* pre = nullptr, size_t pre_offset = 0) {
     if (!out_xy || !out_inf) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
     if (n && !scalars) ZKM_FAIL(ZKM_ERR_ARG, "null scalars");
     const int W = coord_words(curve, group);
     uint64_t* d_scal = (uint64_t*)c->io_scalars.get((n ? n : 1) * 32);
     uint64_t* d_out = (uint64_t*)c->io_out.get((2 * W + 1) * 8);
     h2d(d_scal, scalars, n * 32, c->stream);
-    msm_run(c, curve, group, d_bases, d_inf, d_scal, n, d_out, c->stream);
+    msm_run(c, curve, group, d_bases, d_inf, d_scal, n, d_out, c->stream, pre, pre_offset);
     uint64_t* h = (uint64_t*)c->pin_in.get((2 * W + 1) * 8);
     ZKM_CUDA(cudaMemcpyAsync(h, d_out, (2 * W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     ZKM_CUDA(cudaStreamSynchronize(c->stream));
@@ -150,6 +150,7 @@ void zkm_shutdown(void) {
     for (auto& kv : c->bases) {
         cudaFree(kv.second.d_xy);
         if (kv.second.d_inf) cudaFree(kv.second.d_inf);
+        if (kv.second.d_table) cudaFree(kv.second.d_table);
     }
     c->bases.clear();
     for (auto& e : c->pev)
@@ -189,6 +190,7 @@ static int32_t register_impl(int32_t curve, int32_t group, const uint64_t* xy, c
             ZKM_CUDA(cudaMalloc((void**)&r.d_inf, n ? n : 16));
             if (n) ZKM_CUDA(cudaMemcpyAsync(r.d_inf, inf, n, kind, c->stream));
         }
+        if (c->opt.msm_precompute) msm_precompute(c, &r, c->stream);
         ZKM_CUDA(cudaStreamSynchronize(c->stream));
         uint64_t h = c->next_handle++;
         c->bases[h] = r;
@@ -215,6 +217,7 @@ int32_t zkm_bases_release(uint64_t handle) {
         ZKM_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(it->second.d_xy);
         if (it->second.d_inf) cudaFree(it->second.d_inf);
+        if (it->second.d_table) cudaFree(it->second.d_table);
         c->bases.erase(it);
     });
 }
@@ -236,7 +239,7 @@ int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scala
         const BasesReg& r = lookup(c, handle, offset, n);
         const size_t rec = 2 * coord_words(r.curve, r.group) * 8;
         msm_host(c, r.curve, r.group, (const char*)r.d_xy + offset * rec, r.d_inf ? r.d_inf + offset : nullptr, scalars, n,
-                 out_xy, out_inf);
+                 out_xy, out_inf, &r, offset);
     });
 }
 
@@ -251,7 +254,7 @@ int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t
         const size_t rec = 2 * coord_words(r.curve, r.group) * 8;
         cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
         msm_run(c, r.curve, r.group, (const char*)r.d_xy + offset * rec, r.d_inf ? r.d_inf + offset : nullptr, d_scalars, n,
-                d_out, s);
+                d_out, s, &r, offset);
     });
 }
 
@@ -298,6 +301,40 @@ int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uin
     });
 }
 
+int32_t zkm_witness_map_device(int32_t curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
+                               void* stream) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (!d_a || !d_b || !d_c || !d_h) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        witness_map_run(c, curve, d_a, d_b, d_c, log_n, d_h, stream ? (cudaStream_t)stream : c->stream);
+    });
+}
+
+int32_t zkm_witness_map(int32_t curve, const uint64_t* a, const uint64_t* b, const uint64_t* cc, uint32_t log_n,
+                        uint64_t* h_out) {
+    return guarded([&] {
+        Context* c = ctx();
+        if (!a || !b || !cc || !h_out) ZKM_FAIL(ZKM_ERR_ARG, "null pointer");
+        const int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
+        if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+        if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
+        if (log_n > 28) ZKM_FAIL(ZKM_ERR_ARG, "log_n %u: witness maps above 2^28 are not supported by this build", log_n);
+        std::lock_guard<std::mutex> lk(c->mu);
+        ZKM_CUDA(cudaSetDevice(c->device));
+        const size_t bytes = (size_t)32 << log_n;
+        char* d = (char*)c->io_scalars.get(4 * bytes);
+        h2d(d, a, bytes, c->stream);
+        h2d(d + bytes, b, bytes, c->stream);
+        h2d(d + 2 * bytes, cc, bytes, c->stream);
+        witness_map_run(c, curve, (uint64_t*)d, (uint64_t*)(d + bytes), (uint64_t*)(d + 2 * bytes), log_n,
+                        (uint64_t*)(d + 3 * bytes), c->stream);
+        ZKM_CUDA(cudaMemcpyAsync(h_out, d + 3 * bytes, bytes, cudaMemcpyDeviceToHost, c->stream));
+        ZKM_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
 int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5x4) {
     return guarded([&] {
         Context* c = ctx();
@@ -324,6 +361,8 @@ int32_t zkm_set_option(const char* key, int64_t value) {
             c->opt.ntt_max_radix_log = (int)value;
         } else if (!strcmp(key, "profile")) {
             c->opt.profile = value ? 1 : 0;
+        } else if (!strcmp(key, "msm_precompute")) {
+            c->opt.msm_precompute = value ? 1 : 0;
         } else {
             ZKM_FAIL(ZKM_ERR_ARG, "unknown option '%s'", key);
         }

@@ -95,13 +95,17 @@ struct BasesReg {
     size_t n;
     void* d_xy = nullptr;     // n affine records, 2 * W * 8 bytes each
     uint8_t* d_inf = nullptr; // n flags or nullptr
+    // optional window multiples (option "msm_precompute" at registration): table[w * n + i] = 2^(pre_c w) P_i
+    void* d_table = nullptr;
+    int pre_c = 0, pre_W = 0;
 };
 
 struct Options {
     int msm_window_bits = 0;
     int msm_chunk = 0;
-    int ntt_max_radix_log = 10;
+    int ntt_max_radix_log = 12;
     int profile = 0;  // record CUDA events at the MSM stage boundaries
+    int msm_precompute = 0;  // registrations made while set carry precomputed window multiples
 };
 
 struct Context {
@@ -136,8 +140,11 @@ void ntt_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint3
              cudaStream_t stream);
 void ntt_domain_constants(int curve, uint32_t log_n, uint64_t* out5x4_host);
 void ntt_release(Context* c);
+void witness_map_run(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
+                     cudaStream_t stream);
 void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
-             size_t n, uint64_t* d_out, cudaStream_t stream);
+             size_t n, uint64_t* d_out, cudaStream_t stream, const BasesReg* pre = nullptr, size_t pre_offset = 0);
+void msm_precompute(Context* c, BasesReg* reg, cudaStream_t stream);
 void points_sum_run(Context* c, int curve, int group, const uint64_t* d_points, size_t m, uint64_t* d_out,
                     cudaStream_t stream);
 void testgen_progression(Context* c, int curve, int group, uint64_t a0, uint64_t d, size_t n, uint64_t* d_out,

@@ -65,12 +65,12 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                     carry = 1;
                 }
                 if (d != 0 && (MODE == 0 || w == w_only)) {
-                    uint32_t key = (uint32_t)w * pl.B + (d - 1);
+                    uint32_t key = (uint32_t)w * pl.key_stride + (d - 1);
                     if (MODE == 0) {
                         atomicAdd(&counts_or_cursor[key], 1u);
                     } else {
                         uint32_t pos = atomicAdd(&counts_or_cursor[key], 1u);
-                        idx_out[pos] = (uint32_t)i | (sign << 31);
+                        idx_out[pos] = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (sign << 31);
                     }
                 }
                 w++;
@@ -162,8 +162,8 @@ __global__ void k_tasks_order(const uint32_t* __restrict__ tlen, const uint32_t*
 // ---------------------------------------------------------------------------------- host side
 static int windows_for(int scalar_bits, int c) { return (scalar_bits + 1 + c - 1) / c; }
 
-int msm_auto_window_bits(int curve, int group, size_t n) {
-    (void)group;
+// precomputed != 0: the windows share one bucket set (bases registered with window multiples)
+static int auto_window_bits(int curve, size_t n, int precomputed) {
     const int bits = curve == ZKM_CURVE_BLS12_381 ? 255 : 254;
     if (n < 2) n = 2;
     double best = 1e300;
@@ -173,13 +173,18 @@ int msm_auto_window_bits(int curve, int group, size_t n) {
         double B = (double)(1u << (c - 1));
         // madd = 10 products per (point, window); per bucket: ~3 full adds (14 products) for the
         // running-sum reduction and the partial-sum fold, plus sort/bookkeeping
-        double cost = W * ((double)n * 10.0 + B * 50.0);
+        double cost = precomputed ? W * (double)n * 10.0 + B * 50.0 : W * ((double)n * 10.0 + B * 50.0);
         if (cost < best) {
             best = cost;
             best_c = c;
         }
     }
     return best_c;
+}
+
+int msm_auto_window_bits(int curve, int group, size_t n) {
+    (void)group;
+    return auto_window_bits(curve, n, 0);
 }
 
 static const CurveOps* curve_ops(int curve, int group) {
@@ -202,8 +207,25 @@ static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t
     ZKM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)count, s));
 }
 
+// Window multiples for a registration of n bases: picks the window size once (it is then fixed for every
+// MSM over this registration) and fills reg->d_table.
+void msm_precompute(Context* c, BasesReg* reg, cudaStream_t s) {
+    const CurveOps* ops = curve_ops(reg->curve, reg->group);
+    if (reg->n == 0) return;
+    int cb = c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : auto_window_bits(reg->curve, reg->n, 1);
+    if (cb < 2) cb = 2;
+    if (cb > 24) cb = 24;
+    int W = windows_for(ops->scalar_bits, cb);
+    if ((double)reg->n * W >= 2.0e9) ZKM_FAIL(ZKM_ERR_ARG, "precomputed table of %zu x %d points exceeds 2^31 entries", reg->n, W);
+    const size_t rec = 2 * (size_t)coord_words(reg->curve, reg->group) * 8;
+    ZKM_CUDA(cudaMalloc(&reg->d_table, reg->n * (size_t)W * rec));
+    ops->precompute(s, reg->d_xy, reg->d_inf, (uint64_t)reg->n, cb, W, reg->d_table);
+    reg->pre_c = cb;
+    reg->pre_W = W;
+}
+
 void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
-             size_t n, uint64_t* d_out, cudaStream_t s) {
+             size_t n, uint64_t* d_out, cudaStream_t s, const BasesReg* pre, size_t pre_offset) {
     const CurveOps* ops = curve_ops(curve, group);
     if (n == 0) {
         ops->write_identity(s, d_out);
@@ -212,12 +234,26 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     if (n >= (1ull << 31)) ZKM_FAIL(ZKM_ERR_ARG, "MSM of %zu points: at most 2^31 - 1 supported", n);
     MsmPlan pl;
     pl.scalar_bits = ops->scalar_bits;
-    pl.c = c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : msm_auto_window_bits(curve, group, n);
+    const bool use_pre = pre && pre->d_table;
+    pl.c = use_pre ? pre->pre_c : (c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : msm_auto_window_bits(curve, group, n));
     if (pl.c < 2) pl.c = 2;
     if (pl.c > 24) pl.c = 24;
     pl.W = windows_for(pl.scalar_bits, pl.c);
     pl.B = 1u << (pl.c - 1);
-    pl.K = (uint32_t)pl.W * pl.B;
+    if (use_pre) {          // one bucket set, entries index the table of window multiples
+        pl.K = pl.B;
+        pl.key_stride = 0;
+        pl.idx_stride = (uint32_t)pre->n;
+        pl.idx_base = (uint32_t)pre_offset;
+        pl.RW = 1;
+        d_bases = pre->d_table;
+    } else {
+        pl.K = (uint32_t)pl.W * pl.B;
+        pl.key_stride = pl.B;
+        pl.idx_stride = 0;
+        pl.idx_base = 0;
+        pl.RW = pl.W;
+    }
     if ((double)n * pl.W >= 4.0e9)
         ZKM_FAIL(ZKM_ERR_ARG, "MSM of %zu points x %d windows exceeds 2^32 bucket entries", n, pl.W);
     const uint32_t K = pl.K;
@@ -308,8 +344,8 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     }
 
     mark(4);
-    void* contrib = c->ws[WS_CONTRIB].get(msm_contrib_records(pl.W, pl.B) * XB);
-    void* wsum = c->ws[WS_WSUM].get((size_t)pl.W * XB);
+    void* contrib = c->ws[WS_CONTRIB].get(msm_contrib_records(pl.RW, pl.B) * XB);
+    void* wsum = c->ws[WS_WSUM].get((size_t)pl.RW * XB);
     ops->reduce(s, part[cur], tbase[cur], tpb[cur], pl, contrib, wsum, d_out);
     mark(5);
     c->pev_valid = prof;

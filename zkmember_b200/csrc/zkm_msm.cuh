@@ -11,8 +11,15 @@ struct MsmPlan {
     int c;         // window bits
     int W;         // windows = ceil((scalar_bits + 1) / c)
     uint32_t B;    // buckets per window = 2^(c-1)  (signed digits: |d| in 1..B)
-    uint32_t K;    // W * B
+    uint32_t K;    // number of bucket lists: W * B, or B when the windows share one bucket set
     int scalar_bits;
+    // bucket key = w * key_stride + |d| - 1 ; list entry = w * idx_stride + idx_base + i  (| sign << 31)
+    // plain bases: key_stride = B, idx_stride = 0.  Bases registered with precomputed window multiples
+    // 2^(c w) P_i (table row w): key_stride = 0 (one bucket set for all windows), idx_stride = table row length.
+    uint32_t key_stride;
+    uint32_t idx_stride;
+    uint32_t idx_base;
+    int RW;        // windows seen by the reduction: W, or 1 with precomputed multiples (no Horner doublings)
 };
 
 // Task list of one fold level: task t sums entries [tstart[t], tstart[t] + tlen[t]); threads walk
@@ -38,13 +45,20 @@ struct CurveOps {
     void (*write_identity)(cudaStream_t s, uint64_t* d_out);
     void (*points_sum)(cudaStream_t s, const uint64_t* d_points, uint64_t m, uint64_t* d_out);
     void (*gen_progression)(cudaStream_t s, uint64_t a0, uint64_t d, uint64_t n, void* d_out);
+    // table[w * n + i] = affine(2^(c w) * bases[i]), w < W  (window multiples of registered bases)
+    void (*precompute)(cudaStream_t s, const void* bases, const uint8_t* inf, uint64_t n, int c, int W, void* table);
 };
 
 // buckets per reduction thread: large enough that the lo * run scalar multiple is a small overhead
-inline uint32_t msm_reduce_group(uint32_t B) { return B >= 4096 ? 64u : (B >= 16 ? 16u : B); }
+// (and small enough that a small MSM still spreads over the SMs: the chain of 2 g additions is pure latency)
+inline uint32_t msm_reduce_group(uint32_t B, uint32_t W) {
+    uint32_t g = 64;
+    while (g > 4 && (uint64_t)W * (B / g) < 16384) g >>= 1;
+    return g < B ? g : B;
+}
 // XYZZ records needed by CurveOps::reduce for `contrib`
 inline size_t msm_contrib_records(int W, uint32_t B) {
-    uint32_t per_w = B / msm_reduce_group(B);
+    uint32_t per_w = B / msm_reduce_group(B, (uint32_t)W);
     return (size_t)W * per_w + (size_t)W * ((per_w + 1023) / 1024) + 1;
 }
 

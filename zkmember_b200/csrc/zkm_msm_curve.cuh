@@ -274,6 +274,32 @@ __global__ void __launch_bounds__(128) k_gen_progression(uint64_t a0, uint64_t d
 }
 
 
+// window multiples of registered bases: table[w * n + i] = affine(2^(c w) P_i).  One-time cost at
+// registration (W inversions per base); afterwards every window of an MSM lands in ONE bucket set and
+// the Horner doubling chain of the window combine disappears.
+template <class F>
+__global__ void __launch_bounds__(128) k_precompute(const char* __restrict__ bases, const uint8_t* __restrict__ inf,
+                                                    uint64_t n, int c, int W, char* __restrict__ table) {
+    constexpr int CB = CoordIO<F>::BYTES;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = CoordIO<F>::ld(bases + i * 2 * CB), y = CoordIO<F>::ld(bases + i * 2 * CB + CB);
+    const bool is_inf = inf && inf[i];
+    XYZZ<F> p = xyzz_from_affine(x, y);
+    for (int w = 0; w < W; w++) {
+        if (w > 0) {
+            for (int k = 0; k < c; k++) xyzz_dbl_ni(p);
+            if (is_inf || !xyzz_to_affine_ni(p, x, y)) {
+                x = F::zero();
+                y = F::zero();
+            }
+        }
+        char* dst = table + ((uint64_t)w * n + i) * 2 * CB;
+        CoordIO<F>::st(dst, x);
+        CoordIO<F>::st(dst + CB, y);
+    }
+}
+
 // ---------------------------------------------------------------------------------- ops table
 template <class G>
 struct OpsImpl {
@@ -286,25 +312,23 @@ struct OpsImpl {
     }
     static void reduce(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl,
                        void* contrib, void* wsum, uint64_t* d_out) {
-        uint32_t g = msm_reduce_group(pl.B);
+        const uint32_t RW = (uint32_t)pl.RW;
+        uint32_t g = msm_reduce_group(pl.B, RW);
         uint32_t per_w = pl.B / g;
-        unsigned rblocks = ((unsigned)pl.W * per_w + 127) / 128;
-        ZKM_LAUNCH(k_bucket_reduce<F>, rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, (uint32_t)pl.W, pl.B, g,
+        unsigned rblocks = (RW * per_w + 127) / 128;
+        ZKM_LAUNCH(k_bucket_reduce<F>, rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, RW, pl.B, g,
                    (XYZZ<F>*)contrib);
         // two-step sum of the per-slice contributions of every window: per_w -> nslices -> 1
-        XYZZ<F>* stage = (XYZZ<F>*)contrib + (size_t)pl.W * per_w;
+        XYZZ<F>* stage = (XYZZ<F>*)contrib + (size_t)RW * per_w;
         uint32_t nslices = (per_w + 1023) / 1024;
         if (nslices > 1) {
             uint32_t chunk = (per_w + nslices - 1) / nslices;
-            ZKM_LAUNCH(k_window_sum<F>, (unsigned)pl.W * nslices, 64, 0, s, (const XYZZ<F>*)contrib, per_w, chunk, nslices,
-                       stage);
-            ZKM_LAUNCH(k_window_sum<F>, (unsigned)pl.W, 64, 0, s, (const XYZZ<F>*)stage, nslices, nslices, 1u,
-                       (XYZZ<F>*)wsum);
+            ZKM_LAUNCH(k_window_sum<F>, RW * nslices, 64, 0, s, (const XYZZ<F>*)contrib, per_w, chunk, nslices, stage);
+            ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)stage, nslices, nslices, 1u, (XYZZ<F>*)wsum);
         } else {
-            ZKM_LAUNCH(k_window_sum<F>, (unsigned)pl.W, 64, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u,
-                       (XYZZ<F>*)wsum);
+            ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u, (XYZZ<F>*)wsum);
         }
-        ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.W, pl.c, d_out);
+        ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.RW, pl.c, d_out);
     }
     static void write_identity(cudaStream_t s, uint64_t* d_out) { ZKM_LAUNCH(k_write_identity<F>, 1, 32, 0, s, d_out); }
     static void points_sum(cudaStream_t s, const uint64_t* pts, uint64_t m, uint64_t* d_out) {
@@ -314,6 +338,11 @@ struct OpsImpl {
         if (n == 0) return;
         unsigned blocks = (unsigned)((n + 127) / 128);
         ZKM_LAUNCH(k_gen_progression<G>, blocks, 128, 0, s, a0, d, n, (char*)d_out);
+    }
+    static void precompute(cudaStream_t s, const void* bases, const uint8_t* inf, uint64_t n, int c, int W, void* table) {
+        if (n == 0) return;
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        ZKM_LAUNCH(k_precompute<F>, blocks, 128, 0, s, (const char*)bases, inf, n, c, W, (char*)table);
     }
     static CurveOps make(int curve, int group) {
         CurveOps o;
@@ -327,6 +356,7 @@ struct OpsImpl {
         o.write_identity = write_identity;
         o.points_sum = points_sum;
         o.gen_progression = gen_progression;
+        o.precompute = precompute;
         return o;
     }
 };

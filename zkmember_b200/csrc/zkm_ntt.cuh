@@ -126,6 +126,7 @@ struct NttCfg {
     static constexpr int TILES = NT / TPT;                 // tiles per CTA iteration
     static constexpr int SMEM = NT * 8 * 32;               // bytes
     static constexpr int NR = (R + 2) / 3;                 // register rounds
+    static constexpr int MINB = 512 / NT;                  // 16 warps per SM (<= 128 registers per thread)
 };
 
 __device__ __forceinline__ uint32_t ntt_slot(uint32_t tau, uint32_t q, int pl) {
@@ -164,7 +165,7 @@ __device__ __forceinline__ Fp<P> coset_factor(const NttPassArgs& a, uint64_t idx
 }
 
 template <class P, int R>
-__global__ void __launch_bounds__(NttCfg<R>::NT) k_ntt_pass(const NttPassArgs a) {
+__global__ void __launch_bounds__(NttCfg<R>::NT, NttCfg<R>::MINB) k_ntt_pass(const NttPassArgs a) {
     typedef NttCfg<R> C;
     extern __shared__ uint4 ntt_smem[];
     const uint32_t tl = threadIdx.x / C::TPT;
@@ -284,8 +285,32 @@ __global__ void k_ntt_tiny(const uint32_t* in, uint32_t* out, int k, int inverse
     for (int i = 0; i < n; i++) st_fp<P>(out + i * P::N, y[i]);
 }
 
+// ---------------------------------------------------------------------------------- witness map glue
+// ab[i] = (a[i] * b[i] - c[i]) * zinv,  zinv = 1 / (g^n - 1): the pointwise step of ark-groth16 0.3.0
+// R1CStoQAP::witness_map (src/r1cs_to_qap.rs) between the coset FFTs and the coset iFFT.
+template <class P>
+__global__ void __launch_bounds__(256) k_qap_pointwise(uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                                       const uint32_t* __restrict__ c, const uint32_t* __restrict__ zinv,
+                                                       uint64_t n) {
+    const Fp<P> z = ld_fp<P>(zinv);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        Fp<P> x = ld_fp_plain<P>(a + i * P::N);
+        Fp<P> y = ld_fp<P>(b + i * P::N);
+        Fp<P> w = ld_fp<P>(c + i * P::N);
+        st_fp<P>(a + i * P::N, fp_mul(fp_sub(fp_mul(x, y), w), z));
+    }
+}
+// out[0] = 1 / (g^(2^k) - 1)
+template <class P>
+__global__ void k_vanishing_inv(uint32_t* out, int k) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fp<P> g = fr_const<P>(FrRoots<P>::gen);
+    for (int i = 0; i < k; i++) g = fp_sqr(g);
+    st_fp<P>(out, fp_inv(fp_sub(g, Fp<P>::one())));
+}
+
 // ---------------------------------------------------------------------------------- host side
-enum TableKind : uint64_t { TW = 1, COSET_LO = 2, COSET_HI = 3, DOMAIN = 4 };
+enum TableKind : uint64_t { TW = 1, COSET_LO = 2, COSET_HI = 3, DOMAIN = 4, VANISH = 5 };
 static uint64_t table_key(uint64_t kind, int curve, int k, int inverse) {
     return (kind << 32) | ((uint64_t)curve << 16) | ((uint64_t)inverse << 8) | (uint64_t)k;
 }
@@ -448,6 +473,35 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
         s0 += R;
     }
     if (copy_back) ZKM_CUDA(cudaMemcpyAsync(out, final_dst, n * 32, cudaMemcpyDeviceToDevice, s));
+}
+
+// R1CStoQAP::witness_map on device-resident evaluation vectors a, b, c (each 2^k elements, consumed):
+// h = coset_ifft( (coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / Z_H(g) ).
+template <class P>
+static void witness_map_t(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n,
+                          uint64_t* d_h, cudaStream_t s) {
+    const uint64_t n = 1ull << log_n;
+    uint64_t* tmp = (uint64_t*)c->ntt_b.get(n * 32);
+    uint64_t* vecs[3] = {d_a, d_b, d_c};
+    for (int v = 0; v < 3; v++) {
+        ntt_run_t<P>(c, curve, vecs[v], tmp, log_n, 1, 0, s);   // ifft
+        ntt_run_t<P>(c, curve, tmp, vecs[v], log_n, 0, 1, s);   // coset_fft
+    }
+    uint64_t key = table_key(VANISH, curve, (int)log_n, 0);
+    auto it = c->twiddles.find(key);
+    void* zinv;
+    if (it == c->twiddles.end()) {
+        ZKM_CUDA(cudaMalloc(&zinv, P::N * 4));
+        c->twiddles[key] = zinv;
+        ZKM_LAUNCH(k_vanishing_inv<P>, 1, 32, 0, s, (uint32_t*)zinv, (int)log_n);
+    } else {
+        zinv = it->second;
+    }
+    uint64_t blocks = (n + 255) / 256;
+    uint64_t cap = (uint64_t)c->sm_count * 8;
+    ZKM_LAUNCH(k_qap_pointwise<P>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, (uint32_t*)d_a, (const uint32_t*)d_b,
+               (const uint32_t*)d_c, (const uint32_t*)zinv, n);
+    ntt_run_t<P>(c, curve, d_a, d_h, log_n, 1, 1, s);           // coset_ifft
 }
 
 }  // namespace zkm

@@ -5,6 +5,14 @@ namespace zkm {
 
 void ntt_run_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset, cudaStream_t s);
 void ntt_domain_constants_bn(Context* c, uint32_t* d, int log_n);
+void witness_map_bn(Context* c, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h, cudaStream_t s);
+
+void witness_map_run(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
+                     cudaStream_t s) {
+    if (curve == ZKM_CURVE_BLS12_381) witness_map_t<Bls12_381_FrP>(c, curve, d_a, d_b, d_c, log_n, d_h, s);
+    else if (curve == ZKM_CURVE_BN254) witness_map_bn(c, d_a, d_b, d_c, log_n, d_h, s);
+    else ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+}
 
 void ntt_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
              cudaStream_t stream) {

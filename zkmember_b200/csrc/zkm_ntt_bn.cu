@@ -6,6 +6,9 @@ namespace zkm {
 void ntt_run_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset, cudaStream_t s) {
     ntt_run_t<Bn254_FrP>(c, ZKM_CURVE_BN254, d_in, d_out, log_n, inverse, coset, s);
 }
+void witness_map_bn(Context* c, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h, cudaStream_t s) {
+    witness_map_t<Bn254_FrP>(c, ZKM_CURVE_BN254, d_a, d_b, d_c, log_n, d_h, s);
+}
 void ntt_domain_constants_bn(Context* c, uint32_t* d, int log_n) {
     ZKM_LAUNCH(k_domain_constants<Bn254_FrP>, 1, 32, 0, c->stream, d, log_n);
 }
