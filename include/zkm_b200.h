@@ -100,6 +100,10 @@ int32_t zkm_witness_map(int32_t curve, const uint64_t* a, const uint64_t* b, con
 int32_t zkm_witness_map_device(int32_t curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n,
                                uint64_t* d_h, void* stream);
 
+/* Fr::into_repr() on n device-resident elements (Montgomery -> canonical BigInteger256): the conversion
+ * create_proof applies to h before the h-query MSM (ark-groth16 0.3.0 src/prover.rs).  In place allowed. */
+int32_t zkm_fr_into_repr_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream);
+
 /* Radix2EvaluationDomain::new: the five domain constants, Montgomery, 4 words each:
  * group_gen, group_gen_inv, size_inv, generator (= GENERATOR), generator_inv. */
 int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5x4);
@@ -131,9 +135,10 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
  * windows of later MSMs share one bucket set and the final doubling chain disappears; meant for proving
  * keys / SRS that are reused across many proofs).  Unknown keys fail with ZKM_ERR_ARG. */
 int32_t zkm_set_option(const char* key, int64_t value);
-/* With option "profile" = 1: device time (ms, CUDA events on the launching stream) of the five
- * stages of the last MSM: bucket sort | task lists | bucket accumulation | folds | window reduction. */
-int32_t zkm_profile_last_msm(double* ms_out5);
+/* With option "profile" = 1: device time (ms, CUDA events on the launching stream) of the six stages of
+ * the last MSM: bucket sort | batched-affine pair levels | task lists | XYZZ bucket accumulation | folds |
+ * window reduction. */
+int32_t zkm_profile_last_msm(double* ms_out6);
 /* Kernel launches issued by this library since the last call with reset != 0. */
 uint64_t zkm_launch_count(int32_t reset);
 /* Window bits the automatic choice uses for an n-point MSM (for reports). */

@@ -21,6 +21,7 @@ static void fp_ops(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, 
             case 4: r = sqr(x); break;
             case 5: r = inv(x); break;
             case 6: r = dbl(x); break;
+            case 7: r = fp_inv_fermat(x); break;
             default: r = F::zero();
         }
         memcpy(out + k * N, r.l, 4 * N);

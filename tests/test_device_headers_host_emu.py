@@ -60,6 +60,18 @@ def test_fp_ops(emu, fid):
     assert emu.emu_fp_op(fid, 5, _p(A2), _p(A2), _p(out2), len(nz)) == 0
     for i, a in enumerate(nz):
         assert sum(int(out2[i, j]) << (32 * j) for j in range(n)) == fp.to_mont(pow(a, -1, p))
+    # binary-EGCD inverse == Fermat inverse, incl. 1, p-1, small values and inv(0) = 0
+    edge = [1, 2, 3, p - 1, p - 2, (p + 1) // 2] + [int.from_bytes(rng.bytes(48), "little") % p for _ in range(30)]
+    A3 = np.array([_limbs32(fp.to_mont(v), n) for v in edge], dtype=np.uint32)
+    o5, o7 = np.zeros_like(A3), np.zeros_like(A3)
+    assert emu.emu_fp_op(fid, 5, _p(A3), _p(A3), _p(o5), len(edge)) == 0
+    assert emu.emu_fp_op(fid, 7, _p(A3), _p(A3), _p(o7), len(edge)) == 0
+    assert np.array_equal(o5, o7)
+    for i, a in enumerate(edge):
+        assert sum(int(o5[i, j]) << (32 * j) for j in range(n)) == fp.to_mont(pow(a, -1, p))
+    Z = np.zeros((1, n), dtype=np.uint32)
+    oz = np.ones_like(Z)
+    assert emu.emu_fp_op(fid, 5, _p(Z), _p(Z), _p(oz), 1) == 0 and not oz.any()
 
 
 @pytest.mark.parametrize("curve", [BLS12_381, BN254], ids=lambda c: c.name)

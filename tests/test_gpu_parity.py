@@ -322,3 +322,61 @@ def test_msm_precomputed_window_multiples(zkm, curve, g):
             _check_point(curve, g, got, want_xy, want_inf)
     finally:
         reg.release()
+
+
+# ------------------------------------------------------------------------------- batched-affine pairwise levels
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("g", [1, 2])
+@pytest.mark.parametrize("levels", [1, 3, 9])
+def test_msm_affine_levels_exceptional_pairs(zkm, curve, g, levels):
+    """Forced batched-affine levels on lists built to hit every exceptional pair: P + P (doubling in the
+    batch), P + (-P) (identity marker travelling through later levels), odd lists, single entries."""
+    G = exact.Group(curve, g)
+    base = capi.progression(curve.curve_id, g, 77, 5, 8)
+    neg = []
+    for i in range(8):
+        P = exact.point_from_bytes(curve, g, base[i].tobytes(), 0)
+        b, _ = exact.point_to_bytes(curve, g, G.neg(P))
+        neg.append(np.frombuffer(b, dtype=np.uint64))
+    s = capi.random_scalars(curve.curve_id, 4, seed=levels + g)
+    cases = [
+        ([base[0], base[0]], [s[0], s[0]]),                                   # P + P in every bucket
+        ([base[0], neg[0]], [s[0], s[0]]),                                    # cancels everywhere -> identity
+        ([base[0], base[0], base[0]], [s[1], s[1], s[1]]),                    # odd list of equal points
+        ([base[0], neg[0], base[1]], [s[1], s[1], s[1]]),                     # identity marker + another point
+        ([base[0], base[0], neg[0], neg[0], base[2]], [s[2]] * 5),
+        ([base[i % 8] for i in range(37)], [s[3]] * 37),                      # one long list per window, repeats
+    ]
+    zkm.set_option("msm_affine_levels", levels)
+    zkm.set_option("msm_window_bits", 6)
+    try:
+        for bs, ss in cases:
+            bases = np.stack(bs)
+            scal = np.stack(ss)
+            want_xy, want_inf = capi.msm(curve.curve_id, g, bases, scal)
+            got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal, curve=curve.name, group=g)
+            _check_point(curve, g, got, want_xy, want_inf)
+    finally:
+        zkm.set_option("msm_affine_levels", -1)
+        zkm.set_option("msm_window_bits", 0)
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("levels,kind", [(1, "uniform"), (2, "witness"), (4, "uniform"), (6, "witness"), (12, "small")])
+def test_msm_affine_levels_random(zkm, curve, levels, kind):
+    n = 6000
+    bases = capi.progression(curve.curve_id, 1, 31, 17, n)
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[[1, 500]] = 1
+    bases[41] = bases[40]
+    scal = capi.random_scalars(curve.curve_id, n, seed=levels, kind=kind)
+    scal[41] = scal[40]
+    want_xy, want_inf = capi.msm(curve.curve_id, 1, bases, scal, inf)
+    zkm.set_option("msm_affine_levels", levels)
+    zkm.set_option("msm_window_bits", 7)
+    try:
+        got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal, curve=curve.name, group=1, infinity=inf)
+    finally:
+        zkm.set_option("msm_affine_levels", -1)
+        zkm.set_option("msm_window_bits", 0)
+    _check_point(curve, 1, got, want_xy, want_inf)

@@ -1,0 +1,177 @@
+#!/usr/bin/env python3
+"""zkMember-shaped Groth16 proof PROXY: the MSM + NTT work of one ark-groth16
+`create_proof` on a Merkle-membership circuit of domain size n = 2^log_n -- witness map (7 NTTs +
+pointwise step), h/l/a/b_g1 MSMs on G1 and the b_g2 MSM on G2, with witness-like scalars
+(45 % zero, 45 % one, 10 % uniform) and 50 % points at infinity in the b queries.
+
+It is a proxy: R1CS synthesis (serial host Rust, re-run inside every prove) is NOT included, and the
+real circuit cannot be synthesised here (no arkworks).  Host buffers in, host results out; the proving
+key is registered once (benches/groth16.rs:107-115).  Prints one JSON line.
+
+  python tools/groth16_proxy.py [--log-n 16] [--proofs 20] [--no-precompute] [--cpu]
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import zkmember_b200 as zkm  # noqa: E402
+from zkmember_b200 import _lib  # noqa: E402
+from oracle import capi  # noqa: E402  (input generator / CPU baseline / checker only)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--log-n", type=int, default=16)
+ap.add_argument("--proofs", type=int, default=20)
+ap.add_argument("--no-precompute", action="store_true")
+ap.add_argument("--cpu", action="store_true", help="time the CPU restatement of the same work (1 proof)")
+ap.add_argument("--serial", action="store_true", help="run the five MSMs one after another on one stream")
+ap.add_argument("--curve", default="bls12_381")
+args = ap.parse_args()
+
+cid = {"bls12_381": 0, "bn254": 1}[args.curve]
+log_n = args.log_n
+n = 1 << log_n
+W1 = 6 if cid == 0 else 4
+zkm.init(0)
+L = _lib.lib()
+dev = torch.device("cuda:0")
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)
+sp = ctypes.c_void_p(st.cuda_stream)
+rng = np.random.default_rng(7)
+
+# ---- proving key (static): query vectors with known discrete logs; b queries half infinity
+sizes = {"h": n - 1, "l": int(0.9 * n), "a": n, "b_g1": n, "b_g2": n}
+host_bases = {k: capi.progression(cid, 2 if k == "b_g2" else 1, 1000 + i, 7 + i, m) for i, (k, m) in enumerate(sizes.items())}
+inf = {k: np.zeros(m, dtype=np.uint8) for k, m in sizes.items()}
+for k in ("b_g1", "b_g2"):
+    inf[k][rng.random(sizes[k]) < 0.5] = 1
+inf["a"][rng.random(n) < 0.1] = 1
+if not args.no_precompute:
+    zkm.set_option("msm_precompute", 1)
+t0 = time.perf_counter()
+regs = {k: zkm.RegisteredBases(cid, 2 if k == "b_g2" else 1, host_bases[k], inf[k]) for k in sizes}
+zkm.set_option("msm_precompute", 0)
+reg_s = time.perf_counter() - t0
+
+# ---- per-proof inputs (host, pinned)
+def pinned(a):
+    return torch.from_numpy(a.view(np.int64)).pin_memory()
+
+h_a = pinned(capi.random_field_elements(cid, n, 11))
+h_b = pinned(capi.random_field_elements(cid, n, 12))
+h_c = pinned(capi.random_field_elements(cid, n, 13))
+full = capi.random_scalars(cid, n, 14, "witness")
+h_full = pinned(full)
+d_abc = torch.empty((3, n, 4), dtype=torch.int64, device=dev)
+d_h = torch.empty((n, 4), dtype=torch.int64, device=dev)
+d_full = torch.empty((n, 4), dtype=torch.int64, device=dev)
+recs = {k: torch.zeros((4 * W1 + 1) if k == "b_g2" else (2 * W1 + 1), dtype=torch.int64, device=dev) for k in sizes}
+h_recs = {k: torch.zeros_like(v, device="cpu").pin_memory() for k, v in recs.items()}
+
+
+from concurrent.futures import ThreadPoolExecutor
+
+msm_streams = {k: torch.cuda.Stream(device=dev) for k in sizes}
+pool = ThreadPoolExecutor(max_workers=5)
+MSM_ARGS = {
+    "h": lambda: (d_h.data_ptr(), sizes["h"]),
+    "l": lambda: (d_full.data_ptr() + 32 * (n - sizes["l"]), sizes["l"]),
+    "a": lambda: (d_full.data_ptr(), sizes["a"]),
+    "b_g1": lambda: (d_full.data_ptr(), sizes["b_g1"]),
+    "b_g2": lambda: (d_full.data_ptr(), sizes["b_g2"]),
+}
+
+
+def run_msm(k, stream_handle):
+    ptr, cnt = MSM_ARGS[k]()
+    regs[k].msm_device(ptr, cnt, recs[k].data_ptr(), stream=stream_handle)
+
+
+def prove_once():
+    """One proof: upload a, b, c and the assignment, witness map -> h, five MSMs, download five points.
+    The MSMs are issued from five host threads on five streams (library lanes), so the G2 MSM and the
+    serial tails of the G1 MSMs overlap; --serial issues them back to back on one stream."""
+    d_abc[0].copy_(h_a, non_blocking=True)
+    d_abc[1].copy_(h_b, non_blocking=True)
+    d_abc[2].copy_(h_c, non_blocking=True)
+    d_full.copy_(h_full, non_blocking=True)
+    ev_full = torch.cuda.Event()
+    ev_full.record(st)
+    _lib.check(L.zkm_witness_map_device(cid, ctypes.c_void_p(d_abc[0].data_ptr()), ctypes.c_void_p(d_abc[1].data_ptr()),
+                                        ctypes.c_void_p(d_abc[2].data_ptr()), log_n, ctypes.c_void_p(d_h.data_ptr()), sp))
+    _lib.check(L.zkm_fr_into_repr_device(cid, ctypes.c_void_p(d_h.data_ptr()), ctypes.c_void_p(d_h.data_ptr()), n, sp))
+    if args.serial:
+        for k in sizes:
+            run_msm(k, st.cuda_stream)
+    else:
+        ev_h = torch.cuda.Event()
+        ev_h.record(st)
+        futs = []
+        for k in sizes:
+            msm_streams[k].wait_event(ev_h if k == "h" else ev_full)
+            futs.append(pool.submit(run_msm, k, msm_streams[k].cuda_stream))
+        for f in futs:
+            f.result()
+        for k in sizes:
+            st.wait_stream(msm_streams[k])
+    for k in sizes:
+        h_recs[k].copy_(recs[k], non_blocking=True)
+    torch.cuda.synchronize()
+
+
+for _ in range(3):
+    prove_once()
+_lib.launch_count(reset=True)
+t0 = time.perf_counter()
+for _ in range(args.proofs):
+    prove_once()
+wall = (time.perf_counter() - t0) / args.proofs
+launches = _lib.launch_count() // args.proofs
+
+out = {"op": "groth16_proxy", "curve": args.curve, "log_n": log_n, "precompute": not args.no_precompute, "concurrent_msms": not args.serial,
+       "ms_per_proof": wall * 1e3, "proofs_per_s": 1.0 / wall, "kernel_launches_per_proof": int(launches),
+       "pk_register_s": reg_s, "h2d_bytes_per_proof": int(4 * n * 32), "d2h_bytes_per_proof": int(8 * (4 * (2 * W1 + 1) + 4 * W1 + 1)),
+       "note": "MSM + NTT portion of create_proof only (no R1CS synthesis); synthetic zkMember-shaped sizes"}
+
+# ---- check against the CPU restatement (and time it)
+if args.cpu:
+    t0 = time.perf_counter()
+    hh = capi.witness_map(cid, h_a.numpy().view(np.uint64), h_b.numpy().view(np.uint64), h_c.numpy().view(np.uint64))
+    one = np.zeros((n, 4), dtype=np.uint64)
+    hh_repr = np.stack([capi.field_op(1 if cid == 0 else 3, 4, hh[i]) for i in range(0)]) if False else None
+    t_w = time.perf_counter() - t0
+    res = {}
+    t1 = time.perf_counter()
+    res["l"] = capi.msm(cid, 1, host_bases["l"], full[n - sizes["l"]:], inf["l"])
+    res["a"] = capi.msm(cid, 1, host_bases["a"], full, inf["a"])
+    res["b_g1"] = capi.msm(cid, 1, host_bases["b_g1"], full, inf["b_g1"])
+    res["b_g2"] = capi.msm(cid, 2, host_bases["b_g2"], full, inf["b_g2"])
+    t_m = time.perf_counter() - t1
+    ok = True
+    for k in ("l", "a", "b_g1", "b_g2"):
+        r = h_recs[k].numpy().view(np.uint64)
+        xy, isinf = res[k]
+        ok = ok and bool(r[-1]) == isinf and np.array_equal(r[:-1], xy)
+    # h: witness-map output checked element-wise, its MSM timed with the same dense-scalar cost as a uniform MSM
+    d_chk = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    d_abc[0].copy_(h_a); d_abc[1].copy_(h_b); d_abc[2].copy_(h_c)
+    _lib.check(L.zkm_witness_map_device(cid, ctypes.c_void_p(d_abc[0].data_ptr()), ctypes.c_void_p(d_abc[1].data_ptr()),
+                                        ctypes.c_void_p(d_abc[2].data_ptr()), log_n, ctypes.c_void_p(d_chk.data_ptr()), sp))
+    torch.cuda.synchronize()
+    ok = ok and np.array_equal(d_chk.cpu().numpy().view(np.uint64), hh)
+    t2 = time.perf_counter()
+    capi.msm(cid, 1, host_bases["h"], capi.random_scalars(cid, sizes["h"], 15))
+    t_h = time.perf_counter() - t2
+    cpu_s = t_w + t_m + t_h
+    out.update({"parity_ok": bool(ok), "cpu_ms_per_proof": cpu_s * 1e3, "cpu_proofs_per_s": 1.0 / cpu_s,
+                "cpu_threads": capi.lib().orc_num_threads(),
+                "cpu_kind": "arkworks-0.3.0 algorithms restated in C++ (oracle/cpp)"})
+print(json.dumps(out))

@@ -28,6 +28,7 @@ ap.add_argument("--min", type=int, default=14)
 ap.add_argument("--max", type=int, default=24)
 ap.add_argument("--kind", default="uniform")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--precompute", action="store_true")
 ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle (arkworks algorithm restated) up to 2^20")
 args = ap.parse_args()
 
@@ -63,26 +64,31 @@ if args.what == "msm":
     _lib.check(L.zkm_testgen_progression_device(cid, args.group, 0x1234567, 0x89ABCDE, nmax,
                                                 ctypes.c_void_p(d_bases.data_ptr()), sp))
     torch.cuda.synchronize()
-    reg = zkm.RegisteredBases.from_device(cid, args.group, d_bases.data_ptr(), nmax)
-    del d_bases
+    del_after = True
     d_rec = torch.zeros(2 * W + 1, dtype=torch.int64, device=dev)
     for lg in range(args.min, args.max + 1):
         n = 1 << lg
+        if args.precompute:
+            zkm.set_option("msm_precompute", 1)
+        reg = zkm.RegisteredBases.from_device(cid, args.group, d_bases.data_ptr(), n)   # first n bases
+        zkm.set_option("msm_precompute", 0)
         h = capi.random_scalars(cid, n, seed=0x5EED0000 + lg, kind=args.kind)
         d_s = torch.from_numpy(h.view(np.int64)).to(dev)
         zkm.set_option("profile", 1)
         med, best = timeit(lambda: reg.msm_device(d_s.data_ptr(), n, d_rec.data_ptr(), stream=st.cuda_stream), args.reps)
-        stages = np.zeros(5)
+        stages = np.zeros(6)
         _lib.check(L.zkm_profile_last_msm(ctypes.c_void_p(stages.ctypes.data)))
         row = {"op": "msm", "curve": args.curve, "group": args.group, "log_n": lg, "kind": args.kind, "ms": med,
                "ms_best": best, "window_bits": zkm.msm_window_bits(cid, args.group, n),
-               "stage_ms": dict(zip(["sort", "tasks", "accumulate", "fold", "reduce"], [round(float(v), 4) for v in stages]))}
+               "stage_ms": dict(zip(["sort", "affine", "tasks", "accumulate", "fold", "reduce"], [round(float(v), 4) for v in stages]))}
         if args.cpu and lg <= 20:
             import time
             hb = capi.progression(cid, args.group, 0x1234567, 0x89ABCDE, n)
             t0 = time.perf_counter()
             capi.msm(cid, args.group, hb, h)
             row["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+        row["precompute"] = bool(args.precompute)
+        reg.release()
         print(json.dumps(row), flush=True)
 else:
     for lg in range(args.min, args.max + 1):

@@ -9,8 +9,11 @@ namespace zkm {
 
 static thread_local char t_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
-static Context* g_ctx = nullptr;
+static Shared* g_shared = nullptr;
+static std::vector<Context*> g_lanes;
 static std::mutex g_init_mu;
+static std::mutex g_lane_mu;
+static std::condition_variable g_lane_cv;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -20,8 +23,30 @@ void set_error(const char* fmt, ...) {
 }
 
 Context* ctx() {
-    if (!g_ctx) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
-    return g_ctx;
+    if (g_lanes.empty()) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
+    return g_lanes[0];
+}
+
+Context* acquire_lane() {
+    std::unique_lock<std::mutex> lk(g_lane_mu);
+    if (g_lanes.empty()) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
+    for (;;) {
+        for (Context* c : g_lanes) {
+            if (!c->busy) {
+                c->busy = true;
+                return c;
+            }
+        }
+        g_lane_cv.wait(lk);
+    }
+}
+
+void release_lane(Context* c) {
+    {
+        std::lock_guard<std::mutex> lk(g_lane_mu);
+        c->busy = false;
+    }
+    g_lane_cv.notify_one();
 }
 
 template <class Fn>
@@ -56,6 +81,7 @@ static void msm_host(Context* c, int curve, int group, const void* d_bases, cons
     if (!out_xy || !out_inf) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
     if (n && !scalars) ZKM_FAIL(ZKM_ERR_ARG, "null scalars");
     const int W = coord_words(curve, group);
+    c->begin(c->stream);
     uint64_t* d_scal = (uint64_t*)c->io_scalars.get((n ? n : 1) * 32);
     uint64_t* d_out = (uint64_t*)c->io_out.get((2 * W + 1) * 8);
     h2d(d_scal, scalars, n * 32, c->stream);
@@ -70,12 +96,13 @@ static void msm_host(Context* c, int curve, int group, const void* d_bases, cons
 static int32_t msm_direct(int32_t curve, int group, const uint64_t* bases_xy, const uint8_t* infinity,
                           const uint64_t* scalars, size_t n, uint64_t* out_xy, uint8_t* out_inf) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         check_curve_group(curve, group);
         if (n && !bases_xy) ZKM_FAIL(ZKM_ERR_ARG, "null bases");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
         const int W = coord_words(curve, group);
+        c->begin(c->stream);
         void* d_bases = c->io_bases.get((n ? n : 1) * 2 * W * 8);
         uint8_t* d_inf = nullptr;
         h2d(d_bases, bases_xy, n * 2 * W * 8, c->stream);
@@ -108,8 +135,8 @@ int32_t zkm_device_count(void) {
 int32_t zkm_init(int32_t device) {
     return guarded([&] {
         std::lock_guard<std::mutex> lk(g_init_mu);
-        if (g_ctx) {
-            if (g_ctx->device != device) ZKM_FAIL(ZKM_ERR_ARG, "already bound to device %d (one process per GPU)", g_ctx->device);
+        if (g_shared) {
+            if (g_shared->device != device) ZKM_FAIL(ZKM_ERR_ARG, "already bound to device %d (one process per GPU)", g_shared->device);
             return;
         }
         int count = 0;
@@ -124,41 +151,63 @@ int32_t zkm_init(int32_t device) {
         cudaDeviceProp prop;
         ZKM_CUDA(cudaGetDeviceProperties(&prop, device));
         if (prop.major != 10) ZKM_FAIL(ZKM_ERR_CUDA, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
-        Context* c = new Context();
-        c->device = device;
-        c->sm_count = prop.multiProcessorCount;
-        ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        g_ctx = c;
+        // the MSM gathers 64..192-byte base records at random: fetch 32-byte sectors, not 128-byte lines
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+        cudaGetLastError();
+        Shared* sh = new Shared();
+        sh->device = device;
+        sh->sm_count = prop.multiProcessorCount;
+        std::vector<Context*> lanes;
+        for (int i = 0; i < ZKM_NUM_LANES; i++) {
+            Context* c = new Context(sh);
+            c->lane_id = i;
+            ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            lanes.push_back(c);
+        }
+        std::lock_guard<std::mutex> ll(g_lane_mu);
+        g_shared = sh;
+        g_lanes = lanes;
     });
 }
 
 void zkm_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_init_mu);
-    Context* c = g_ctx;
-    if (!c) return;
-    cudaSetDevice(c->device);
+    Shared* sh = g_shared;
+    if (!sh) return;
+    cudaSetDevice(sh->device);
     cudaDeviceSynchronize();
-    ntt_release(c);
-    for (auto& b : c->ws) b.release();
-    c->io_scalars.release();
-    c->io_bases.release();
-    c->io_inf.release();
-    c->io_out.release();
-    c->pin_in.release();
-    c->pin_out.release();
-    for (auto& kv : c->bases) {
+    std::vector<Context*> lanes;
+    {
+        std::lock_guard<std::mutex> ll(g_lane_mu);
+        lanes.swap(g_lanes);
+        g_shared = nullptr;
+    }
+    for (Context* c : lanes) {
+        c->ntt_a.release();
+        c->ntt_b.release();
+        for (auto& b : c->ws) b.release();
+        c->io_scalars.release();
+        c->io_bases.release();
+        c->io_inf.release();
+        c->io_out.release();
+        c->pin_in.release();
+        c->pin_out.release();
+        for (auto& e : c->pev)
+            if (e) cudaEventDestroy(e);
+        if (c->done_ev) cudaEventDestroy(c->done_ev);
+        cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->copy_stream);
+        delete c;
+    }
+    ntt_release_tables(sh);
+    for (auto& kv : sh->bases) {
         cudaFree(kv.second.d_xy);
         if (kv.second.d_inf) cudaFree(kv.second.d_inf);
         if (kv.second.d_table) cudaFree(kv.second.d_table);
     }
-    c->bases.clear();
-    for (auto& e : c->pev)
-        if (e) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->copy_stream);
-    g_ctx = nullptr;
-    delete c;
+    sh->bases.clear();
+    delete sh;
 }
 
 int32_t zkm_msm_g1(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity, const uint64_t* scalars, size_t n,
@@ -173,11 +222,11 @@ int32_t zkm_msm_g2(int32_t curve, const uint64_t* bases_xy, const uint8_t* infin
 static int32_t register_impl(int32_t curve, int32_t group, const uint64_t* xy, const uint8_t* inf, size_t n,
                              uint64_t* handle_out, cudaMemcpyKind kind) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         check_curve_group(curve, group);
         if (!handle_out) ZKM_FAIL(ZKM_ERR_ARG, "null handle_out");
         if (n && !xy) ZKM_FAIL(ZKM_ERR_ARG, "null bases");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
         BasesReg r;
         r.curve = curve;
@@ -192,6 +241,7 @@ static int32_t register_impl(int32_t curve, int32_t group, const uint64_t* xy, c
         }
         if (c->opt.msm_precompute) msm_precompute(c, &r, c->stream);
         ZKM_CUDA(cudaStreamSynchronize(c->stream));
+        std::lock_guard<std::mutex> rl(c->sh->reg_mu);
         uint64_t h = c->next_handle++;
         c->bases[h] = r;
         *handle_out = h;
@@ -209,12 +259,13 @@ int32_t zkm_bases_register_device(int32_t curve, int32_t group, const uint64_t* 
 
 int32_t zkm_bases_release(uint64_t handle) {
     return guarded([&] {
-        Context* c = ctx();
-        std::lock_guard<std::mutex> lk(c->mu);
+        LaneGuard lane;
+        Context* c = lane.c;
+        ZKM_CUDA(cudaSetDevice(c->device));
+        ZKM_CUDA(cudaDeviceSynchronize());   // no lane may still be reading the bases
+        std::lock_guard<std::mutex> rl(c->sh->reg_mu);
         auto it = c->bases.find(handle);
         if (it == c->bases.end()) ZKM_FAIL(ZKM_ERR_HANDLE, "unknown bases handle %llu", (unsigned long long)handle);
-        ZKM_CUDA(cudaSetDevice(c->device));
-        ZKM_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(it->second.d_xy);
         if (it->second.d_inf) cudaFree(it->second.d_inf);
         if (it->second.d_table) cudaFree(it->second.d_table);
@@ -222,7 +273,8 @@ int32_t zkm_bases_release(uint64_t handle) {
     });
 }
 
-static const BasesReg& lookup(Context* c, uint64_t handle, size_t offset, size_t n) {
+static BasesReg lookup(Context* c, uint64_t handle, size_t offset, size_t n) {
+    std::lock_guard<std::mutex> rl(c->sh->reg_mu);
     auto it = c->bases.find(handle);
     if (it == c->bases.end()) ZKM_FAIL(ZKM_ERR_HANDLE, "unknown bases handle %llu", (unsigned long long)handle);
     if (offset > it->second.n || n > it->second.n - offset)
@@ -233,10 +285,10 @@ static const BasesReg& lookup(Context* c, uint64_t handle, size_t offset, size_t
 int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scalars, size_t n, uint64_t* out_xy,
                            uint8_t* out_inf) {
     return guarded([&] {
-        Context* c = ctx();
-        std::lock_guard<std::mutex> lk(c->mu);
+        LaneGuard lane;
+        Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
-        const BasesReg& r = lookup(c, handle, offset, n);
+        const BasesReg r = lookup(c, handle, offset, n);
         const size_t rec = 2 * coord_words(r.curve, r.group) * 8;
         msm_host(c, r.curve, r.group, (const char*)r.d_xy + offset * rec, r.d_inf ? r.d_inf + offset : nullptr, scalars, n,
                  out_xy, out_inf, &r, offset);
@@ -246,25 +298,27 @@ int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scala
 int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n, uint64_t* d_out,
                                   void* stream) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         if (!d_out || (n && !d_scalars)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
-        const BasesReg& r = lookup(c, handle, offset, n);
+        const BasesReg r = lookup(c, handle, offset, n);
         const size_t rec = 2 * coord_words(r.curve, r.group) * 8;
         cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+        c->begin(s);
         msm_run(c, r.curve, r.group, (const char*)r.d_xy + offset * rec, r.d_inf ? r.d_inf + offset : nullptr, d_scalars, n,
                 d_out, s, &r, offset);
+        c->end(s);
     });
 }
 
 int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_points, size_t m, uint64_t* d_out,
                               void* stream) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         check_curve_group(curve, group);
         if (!d_out || (m && !d_points)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
         points_sum_run(c, curve, group, d_points, m, d_out, stream ? (cudaStream_t)stream : c->stream);
     });
@@ -272,15 +326,16 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
 
 int32_t zkm_ntt(int32_t curve, uint64_t* data, uint32_t log_n, int32_t inverse, int32_t coset) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
         if (!data) ZKM_FAIL(ZKM_ERR_ARG, "null data");
         const int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
         if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
         if (log_n > 30) ZKM_FAIL(ZKM_ERR_ARG, "log_n %u: domains above 2^30 are not supported by this build", log_n);
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
         const size_t bytes = (size_t)32 << log_n;
+        c->begin(c->stream);
         uint64_t* d_a = (uint64_t*)c->io_scalars.get(bytes);
         uint64_t* d_b = (uint64_t*)c->ntt_b.get(bytes);
         h2d(d_a, data, bytes, c->stream);
@@ -293,37 +348,54 @@ int32_t zkm_ntt(int32_t curve, uint64_t* data, uint32_t log_n, int32_t inverse, 
 int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int32_t inverse,
                        int32_t coset, void* stream) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         if (!d_in || !d_out) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
-        ntt_run(c, curve, d_in, d_out, log_n, inverse != 0, coset != 0, stream ? (cudaStream_t)stream : c->stream);
+        cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+        c->begin(s);
+        ntt_run(c, curve, d_in, d_out, log_n, inverse != 0, coset != 0, s);
+        c->end(s);
+    });
+}
+
+int32_t zkm_fr_into_repr_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream) {
+    return guarded([&] {
+        LaneGuard lane;
+        Context* c = lane.c;
+        if (n && (!d_in || !d_out)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
+        ZKM_CUDA(cudaSetDevice(c->device));
+        fr_into_repr_run(c, curve, d_in, d_out, (uint64_t)n, stream ? (cudaStream_t)stream : c->stream);
     });
 }
 
 int32_t zkm_witness_map_device(int32_t curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
                                void* stream) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         if (!d_a || !d_b || !d_c || !d_h) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
-        witness_map_run(c, curve, d_a, d_b, d_c, log_n, d_h, stream ? (cudaStream_t)stream : c->stream);
+        cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+        c->begin(s);
+        witness_map_run(c, curve, d_a, d_b, d_c, log_n, d_h, s);
+        c->end(s);
     });
 }
 
 int32_t zkm_witness_map(int32_t curve, const uint64_t* a, const uint64_t* b, const uint64_t* cc, uint32_t log_n,
                         uint64_t* h_out) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         if (!a || !b || !cc || !h_out) ZKM_FAIL(ZKM_ERR_ARG, "null pointer");
         const int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
         if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
         if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
         if (log_n > 28) ZKM_FAIL(ZKM_ERR_ARG, "log_n %u: witness maps above 2^28 are not supported by this build", log_n);
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
         const size_t bytes = (size_t)32 << log_n;
+        c->begin(c->stream);
         char* d = (char*)c->io_scalars.get(4 * bytes);
         h2d(d, a, bytes, c->stream);
         h2d(d + bytes, b, bytes, c->stream);
@@ -337,19 +409,20 @@ int32_t zkm_witness_map(int32_t curve, const uint64_t* a, const uint64_t* b, con
 
 int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5x4) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         if (!out5x4) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
-        ntt_domain_constants(curve, log_n, out5x4);
+        c->begin(c->stream);
+        ntt_domain_constants(c, curve, log_n, out5x4);
     });
 }
 
 int32_t zkm_set_option(const char* key, int64_t value) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         if (!key) ZKM_FAIL(ZKM_ERR_ARG, "null key");
-        std::lock_guard<std::mutex> lk(c->mu);
         if (!strcmp(key, "msm_window_bits")) {
             if (value < 0 || value > 24) ZKM_FAIL(ZKM_ERR_ARG, "msm_window_bits must be 0 (auto) or 2..24");
             c->opt.msm_window_bits = (int)value;
@@ -361,6 +434,9 @@ int32_t zkm_set_option(const char* key, int64_t value) {
             c->opt.ntt_max_radix_log = (int)value;
         } else if (!strcmp(key, "profile")) {
             c->opt.profile = value ? 1 : 0;
+        } else if (!strcmp(key, "msm_affine_levels")) {
+            if (value < -1 || value > 24) ZKM_FAIL(ZKM_ERR_ARG, "msm_affine_levels must be -1 (auto) or 0..24");
+            c->opt.msm_affine_levels = (int)value;
         } else if (!strcmp(key, "msm_precompute")) {
             c->opt.msm_precompute = value ? 1 : 0;
         } else {
@@ -369,15 +445,16 @@ int32_t zkm_set_option(const char* key, int64_t value) {
     });
 }
 
-int32_t zkm_profile_last_msm(double* ms_out5) {
+int32_t zkm_profile_last_msm(double* ms_out6) {
     return guarded([&] {
-        Context* c = ctx();
-        if (!ms_out5) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
-        std::lock_guard<std::mutex> lk(c->mu);
+        LaneGuard lane;
+        Context* c = lane.c;
+        double* ms_out5 = ms_out6;
+        if (!ms_out6) ZKM_FAIL(ZKM_ERR_ARG, "null output pointer");
         if (!c->pev_valid) ZKM_FAIL(ZKM_ERR_ARG, "no profiled MSM yet (set option \"profile\" to 1 first)");
         ZKM_CUDA(cudaSetDevice(c->device));
-        ZKM_CUDA(cudaEventSynchronize(c->pev[5]));
-        for (int i = 0; i < 5; i++) {
+        ZKM_CUDA(cudaEventSynchronize(c->pev[6]));
+        for (int i = 0; i < 6; i++) {
             float ms = 0.f;
             ZKM_CUDA(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
             ms_out5[i] = ms;
@@ -392,17 +469,17 @@ uint64_t zkm_launch_count(int32_t reset) {
 }
 
 int32_t zkm_msm_window_bits(int32_t curve, int32_t group, size_t n) {
-    if (g_ctx && g_ctx->opt.msm_window_bits > 0) return g_ctx->opt.msm_window_bits;
+    if (g_shared && g_shared->opt.msm_window_bits > 0) return g_shared->opt.msm_window_bits;
     return msm_auto_window_bits(curve, group, n);
 }
 
 int32_t zkm_testgen_progression_device(int32_t curve, int32_t group, uint64_t a0, uint64_t d, size_t n,
                                        uint64_t* d_bases_xy, void* stream) {
     return guarded([&] {
-        Context* c = ctx();
+        LaneGuard lane;
+        Context* c = lane.c;
         check_curve_group(curve, group);
         if (n && !d_bases_xy) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        std::lock_guard<std::mutex> lk(c->mu);
         ZKM_CUDA(cudaSetDevice(c->device));
         testgen_progression(c, curve, group, a0, d, n, d_bases_xy, stream ? (cudaStream_t)stream : c->stream);
     });

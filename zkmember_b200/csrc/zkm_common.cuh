@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <string>
@@ -106,31 +107,71 @@ struct Options {
     int ntt_max_radix_log = 12;
     int profile = 0;  // record CUDA events at the MSM stage boundaries
     int msm_precompute = 0;  // registrations made while set carry precomputed window multiples
+    int msm_affine_levels = -1;  // batched-affine pairwise levels before the XYZZ tasks (-1 = automatic)
 };
 
-struct Context {
+// State shared by all lanes of the process (one process per GPU).
+struct Shared {
     int device = -1;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
-    std::mutex mu;
     Options opt;
-    // NTT state
-    std::map<uint64_t, void*> twiddles;  // key -> device table
-    DevBuf ntt_a, ntt_b;
-    // MSM workspace
-    DevBuf ws[24];
-    DevBuf io_scalars, io_bases, io_inf, io_out;
-    PinnedBuf pin_in, pin_out;
+    std::mutex tw_mu;                      // guards `twiddles`
+    std::map<uint64_t, void*> twiddles;    // key -> device table (twiddles, coset powers, domain constants)
+    std::mutex reg_mu;                     // guards `bases` / `next_handle`
     std::map<uint64_t, BasesReg> bases;
     uint64_t next_handle = 1;
-    // stage timing of the last MSM (opt.profile): events at the boundaries of
-    // sort | task lists | bucket accumulation | fold levels | window reduction
-    cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool pev_valid = false;
 };
 
-Context* ctx();            // throws ZKM_ERR_NOT_INIT when zkm_init has not succeeded
+// A lane = one stream + one set of workspaces.  Every compute call borrows a free lane for its duration,
+// so independent calls from different host threads (e.g. the five MSMs of a Groth16 proof, the G2 MSM next
+// to the G1 ones) run concurrently on the GPU instead of queueing behind one another's serial tails.
+struct Context {
+    Shared* sh;
+    int& device;
+    int& sm_count;
+    Options& opt;
+    std::map<uint64_t, void*>& twiddles;
+    std::map<uint64_t, BasesReg>& bases;
+    uint64_t& next_handle;
+    explicit Context(Shared* s)
+        : sh(s), device(s->device), sm_count(s->sm_count), opt(s->opt), twiddles(s->twiddles), bases(s->bases),
+          next_handle(s->next_handle) {}
+    int lane_id = 0;
+    bool busy = false;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    DevBuf ntt_a, ntt_b;
+    DevBuf ws[40];
+    DevBuf io_scalars, io_bases, io_inf, io_out;
+    PinnedBuf pin_in, pin_out;
+    // stage timing of the last MSM on this lane (opt.profile): events at the boundaries of
+    // sort | affine pair levels | task lists | bucket accumulation | fold levels | window reduction
+    cudaEvent_t pev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool pev_valid = false;
+    // The lane's workspaces may still be in use by kernels enqueued on the stream of its previous borrower:
+    // every call orders itself after `done_ev` and re-records it when it has enqueued its work.
+    cudaEvent_t done_ev = nullptr;
+    void begin(cudaStream_t s) {
+        if (done_ev) ZKM_CUDA(cudaStreamWaitEvent(s, done_ev, 0));
+    }
+    void end(cudaStream_t s) {
+        if (!done_ev) ZKM_CUDA(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
+        ZKM_CUDA(cudaEventRecord(done_ev, s));
+    }
+};
+
+constexpr int ZKM_NUM_LANES = 6;
+Context* acquire_lane();           // blocks until a lane is free; throws ZKM_ERR_NOT_INIT before zkm_init
+void release_lane(Context* c);
+struct LaneGuard {
+    Context* c;
+    LaneGuard() : c(acquire_lane()) {}
+    ~LaneGuard() { release_lane(c); }
+    LaneGuard(const LaneGuard&) = delete;
+    LaneGuard& operator=(const LaneGuard&) = delete;
+};
+
+Context* ctx();            // lane 0 (non-compute queries); throws ZKM_ERR_NOT_INIT when zkm_init has not succeeded
 inline int coord_words(int curve, int group) {
     return (curve == ZKM_CURVE_BLS12_381 ? 6 : 4) * (group == 2 ? 2 : 1);
 }
@@ -138,8 +179,9 @@ inline int coord_words(int curve, int group) {
 // entry points implemented by the two compute translation units
 void ntt_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
              cudaStream_t stream);
-void ntt_domain_constants(int curve, uint32_t log_n, uint64_t* out5x4_host);
-void ntt_release(Context* c);
+void ntt_domain_constants(Context* c, int curve, uint32_t log_n, uint64_t* out5x4_host);
+void ntt_release_tables(Shared* sh);
+void fr_into_repr_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t stream);
 void witness_map_run(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
                      cudaStream_t stream);
 void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,

@@ -80,6 +80,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
     }
 }
 
+// len_out[k] = ceil(len_in[k] / 2) with len_in[k] = off_in[k+1] - off_in[k]  (one pairwise level)
+__global__ void k_pair_lens(const uint32_t* __restrict__ off_in, uint32_t K, uint32_t* __restrict__ len_out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) len_out[k] = (off_in[k + 1] - off_in[k] + 1) >> 1;
+    else if (k == K) len_out[k] = 0;
+}
+
 // ---------------------------------------------------------------------------------- task building
 // tpb[k] = ceil(cnt[k] / L); flags[0] = max cnt
 __global__ void k_tasks_count(const uint32_t* __restrict__ cnt, uint32_t K, uint32_t L, uint32_t* __restrict__ tpb,
@@ -197,7 +204,8 @@ static const CurveOps* curve_ops(int curve, int group) {
 
 enum WsSlot {
     WS_COUNTS = 0, WS_OFF, WS_CURSOR, WS_IDX, WS_TPB_A, WS_TBASE_A, WS_TPB_B, WS_TBASE_B, WS_TSTART, WS_TLEN,
-    WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_PART_B, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP
+    WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_PART_B, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP,
+    WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2
 };
 
 static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t count, cudaStream_t s) {
@@ -307,9 +315,53 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
                    idx, flags);
 
     mark(1);
-    // level-1 task list
     const unsigned kblocks = (K + 1 + 255) / 256;
-    ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, counts, K, L1, tpb[0], flags);
+    // ---- batched-affine pairwise levels (large MSMs): halve every bucket list n_aff times
+    const uint32_t* cur_off = off;       // offsets / lengths / source of the current bucket lists
+    const uint32_t* cur_cnt = counts;
+    const void* cur_src = d_bases;
+    const uint32_t* cur_idx = idx;
+    {
+        int n_aff = c->opt.msm_affine_levels;
+        if (n_aff < 0) {
+            n_aff = 0;
+            if (entries >= (48u << 20)) {   // avg list length 2^a -> a - 1 levels leave ~2 entries per list
+                double avg = (double)entries / (double)K;
+                while (n_aff < 6 && avg >= 4.0) {
+                    avg *= 0.5;
+                    n_aff++;
+                }
+            }
+        }
+        const size_t CBy = ops->coord_bytes;
+        const uint32_t m = 64, m2 = 32;
+        size_t Eb = entries;
+        int p = 0;
+        for (int lvl = 0; lvl < n_aff; lvl++) {
+            const size_t Eout = (Eb + (K < Eb ? K : Eb)) / 2 + 1;      // bound on the outputs of this level
+            const size_t nT = (Eout + m - 1) / m, nU = (nT + m2 - 1) / m2;
+            uint32_t* aoff = c->ws[p ? WS_AOFF_B : WS_AOFF_A].as<uint32_t>(K + 1);
+            uint32_t* alen = c->ws[p ? WS_ALEN_B : WS_ALEN_A].as<uint32_t>(K + 1);
+            char* pt = (char*)c->ws[p ? WS_PT_B : WS_PT_A].get(Eout * 2 * CBy);
+            char* pre = (char*)c->ws[WS_PRE].get(Eout * CBy);
+            char* Tt = (char*)c->ws[WS_T].get((nT + 1) * CBy);
+            char* pre2 = (char*)c->ws[WS_PRE2].get((nT + 1) * CBy);
+            ZKM_LAUNCH(k_pair_lens, kblocks, 256, 0, s, cur_off, K, alen);
+            exclusive_scan(c, alen, aoff, K + 1, s);
+            ops->pair_fwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt);
+            ops->pair_inv((unsigned)c->sm_count, nU, s, aoff, K, m, m2, Tt, pre2);
+            ops->pair_bwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt, pt);
+            cur_off = aoff;
+            cur_cnt = alen;
+            cur_src = pt;
+            cur_idx = nullptr;
+            Eb = Eout;
+            p ^= 1;
+        }
+    }
+    mark(2);
+    // level-1 task list
+    ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, cur_cnt, K, L1, tpb[0], flags);
     exclusive_scan(c, tpb[0], tbase[0], K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(h_flags, flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     ZKM_CUDA(cudaStreamSynchronize(s));  // the one host sync: largest bucket -> depth of the fold tree
@@ -326,11 +378,11 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     };
     // 256 threads, one CTA per SM (the accumulators are register-bound), persistent over the task list
     const unsigned grid_acc = (unsigned)c->sm_count;
-    build_tasks(tbase[0], off, counts, L1);
-    mark(2);
-    ops->accum_affine(grid_acc, s, d_bases, idx, TaskList{tstart, tlen, order, tbase[0], K}, part[0]);
-
+    build_tasks(tbase[0], cur_off, cur_cnt, L1);
     mark(3);
+    ops->accum_affine(grid_acc, s, cur_src, cur_idx, TaskList{tstart, tlen, order, tbase[0], K}, part[0]);
+
+    mark(4);
     int cur = 0;  // tpb[cur] / tbase[cur] / part[cur] describe the current partial sums
     uint32_t maxseg = (maxcnt + L1 - 1) / L1;
     while (maxseg > 1) {
@@ -343,11 +395,11 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         maxseg = (maxseg + L2 - 1) / L2;
     }
 
-    mark(4);
+    mark(5);
     void* contrib = c->ws[WS_CONTRIB].get(msm_contrib_records(pl.RW, pl.B) * XB);
     void* wsum = c->ws[WS_WSUM].get((size_t)pl.RW * XB);
     ops->reduce(s, part[cur], tbase[cur], tpb[cur], pl, contrib, wsum, d_out);
-    mark(5);
+    mark(6);
     c->pev_valid = prof;
 }
 

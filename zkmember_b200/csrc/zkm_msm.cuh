@@ -47,6 +47,16 @@ struct CurveOps {
     void (*gen_progression)(cudaStream_t s, uint64_t a0, uint64_t d, uint64_t n, void* d_out);
     // table[w * n + i] = affine(2^(c w) * bases[i]), w < W  (window multiples of registered bases)
     void (*precompute)(cudaStream_t s, const void* bases, const uint8_t* inf, uint64_t n, int c, int W, void* table);
+    // batched-affine pairwise level (zkm_msm_affine.cuh): denominators + prefix products, inversion of the
+    // per-thread totals, unwind + affine additions into the next level's array
+    void (*pair_fwd)(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
+                     const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T);
+    void (*pair_inv)(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
+                     uint32_t m2, void* T, void* pre2);
+    void (*pair_bwd)(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
+                     const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
+                     void* dst);
+    size_t coord_bytes;
 };
 
 // buckets per reduction thread: large enough that the lo * run scalar multiple is a small overhead

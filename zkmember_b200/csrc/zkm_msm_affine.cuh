@@ -1,0 +1,207 @@
+// zkm_msm_affine.cuh -- batched-affine pairwise reduction of the bucket lists (K4, large MSMs).
+//
+// Instead of chaining XYZZ mixed additions (10 field products per point), the sorted bucket lists are
+// halved level by level with AFFINE additions: out[j] = in[2j] + in[2j+1] inside every bucket.  All
+// additions of a level are independent, so their denominators (x1 - x0, or 2 y0 for a doubling) are
+// inverted together with Montgomery's trick, two storeys high:
+//
+//   k_pair_fwd   thread t walks m consecutive outputs: d_e, exclusive prefix products pre[e] -> HBM,
+//                thread total T[t]
+//   k_inv_batch  thread u owns m2 consecutive totals: prefix products, ONE Fermat inversion, unwind ->
+//                T[t] := 1 / T[t]
+//   k_pair_bwd   thread t unwinds its range backwards: 1/d_e = run * pre[e], run *= d_e, then
+//                lambda = (y1 - y0) / d, x3 = lambda^2 - x0 - x1, y3 = lambda (x0 - x3) - y0 -> next level
+//
+// = 6 field products per addition + 1/(m m2) of an inversion, against 10 for the XYZZ chain; the price is
+// HBM traffic (~0.5 KB per addition, far below the roofline of this integer-bound kernel).  Exceptional
+// pairs are exact: P + P doubles (denominator 2y), P + (-P) yields the identity marker, identity
+// operands pass the other point through.  Identity marker in the affine arrays: top limb of x all ones
+// (no reduced field element has it).  After a few levels the short remaining lists go to the XYZZ
+// task kernels.  The affine result of each bucket is unique, so the final MSM bytes do not change.
+#pragma once
+#include "zkm_msm.cuh"
+
+namespace zkm {
+
+template <class P> __device__ __forceinline__ bool aff_is_identity(const Fp<P>& x) { return x.l[P::N - 1] == 0xffffffffu; }
+template <class P> __device__ __forceinline__ bool aff_is_identity(const Fp2<P>& x) { return x.c0.l[P::N - 1] == 0xffffffffu; }
+template <class P> __device__ __forceinline__ void aff_set_identity(Fp<P>& x, Fp<P>& y) {
+#pragma unroll
+    for (int i = 0; i < P::N; i++) { x.l[i] = 0xffffffffu; y.l[i] = 0; }
+}
+template <class P> __device__ __forceinline__ void aff_set_identity(Fp2<P>& x, Fp2<P>& y) {
+    aff_set_identity(x.c0, y.c0);
+    x.c1 = Fp<P>::zero();
+    y.c1 = Fp<P>::zero();
+}
+
+// position of input i of the current level: level 0 reads the sorted (index | sign) list and gathers the
+// registered bases; later levels read the affine array written by the previous level
+template <class F, bool L0>
+__device__ __forceinline__ const char* pair_src(const char* src, const uint32_t* idx, uint32_t i, uint32_t& sign) {
+    constexpr int CB = CoordIO<F>::BYTES;
+    if (L0) {
+        uint32_t id = idx[i];
+        sign = id >> 31;
+        return src + (size_t)(id & 0x7fffffffu) * (2 * CB);
+    }
+    sign = 0;
+    return src + (size_t)i * (2 * CB);
+}
+
+struct PairCursor {  // bucket of the current output element
+    uint32_t k, lo, hi;
+};
+__device__ __forceinline__ void cursor_seek(PairCursor& c, const uint32_t* __restrict__ off_out, uint32_t K, uint32_t e) {
+    uint32_t a = 0, b = K;  // off_out[a] <= e < off_out[b]
+    while (b - a > 1) {
+        uint32_t mid = (a + b) >> 1;
+        if (off_out[mid] <= e) a = mid; else b = mid;
+    }
+    c.k = a;
+    c.lo = off_out[a];
+    c.hi = off_out[a + 1];
+}
+
+// classification of one output element
+struct PairKind {
+    bool pair;      // two inputs (else: the odd element of the list is passed through)
+    bool has_d;     // contributes a denominator to the batch
+    bool dbl;       // P + P
+    bool cancel;    // P + (-P)
+    bool inf0, inf1;
+};
+
+template <class F, bool L0>
+__global__ void __launch_bounds__(256)
+k_pair_fwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off_in,
+           const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, char* __restrict__ pre, char* __restrict__ T) {
+    constexpr int CB = CoordIO<F>::BYTES;
+    const uint32_t E = off_out[K];
+    const uint32_t nT = (E + m - 1) / m;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nT; t += gridDim.x * blockDim.x) {
+        const uint32_t e0 = t * m, e1 = (e0 + m < E) ? e0 + m : E;
+        PairCursor c;
+        cursor_seek(c, off_out, K, e0);
+        uint32_t ib = off_in[c.k], ie = off_in[c.k + 1];
+        F run = F::one();
+        for (uint32_t e = e0; e < e1; e++) {
+            while (e >= c.hi) {
+                c.k++;
+                c.lo = c.hi;
+                c.hi = off_out[c.k + 1];
+                ib = ie;
+                ie = off_in[c.k + 1];
+            }
+            const uint32_t i0 = ib + 2 * (e - c.lo);
+            CoordIO<F>::st(pre + (size_t)e * CB, run);
+            if (i0 + 1 < ie) {
+                uint32_t s0, s1;
+                const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
+                const char* p1 = pair_src<F, L0>(src, idx, i0 + 1, s1);
+                F x0 = CoordIO<F>::ld_plain(p0), x1 = CoordIO<F>::ld_plain(p1);
+                if (!aff_is_identity(x0) && !aff_is_identity(x1)) {
+                    if (x0 != x1) {
+                        run = run * (x1 - x0);
+                    } else {
+                        F y0 = CoordIO<F>::ld_plain(p0 + CB), y1 = CoordIO<F>::ld_plain(p1 + CB);
+                        if (s0) y0 = neg(y0);
+                        if (s1) y1 = neg(y1);
+                        if (y0 == y1) run = run * dbl(y0);
+                    }
+                }
+            }
+        }
+        CoordIO<F>::st(T + (size_t)t * CB, run);
+    }
+}
+
+// T[i] := 1 / T[i] for i < nT = ceil(E / m)
+template <class F>
+__global__ void __launch_bounds__(128)
+k_inv_batch(const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, uint32_t m2, char* __restrict__ T,
+            char* __restrict__ pre2) {
+    constexpr int CB = CoordIO<F>::BYTES;
+    const uint32_t E = off_out[K];
+    const uint32_t nT = (E + m - 1) / m;
+    const uint32_t nU = (nT + m2 - 1) / m2;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nU; u += gridDim.x * blockDim.x) {
+        const uint32_t i0 = u * m2, i1 = (i0 + m2 < nT) ? i0 + m2 : nT;
+        F run = F::one();
+        for (uint32_t i = i0; i < i1; i++) {
+            CoordIO<F>::st(pre2 + (size_t)i * CB, run);
+            run = run * CoordIO<F>::ld_plain(T + (size_t)i * CB);
+        }
+        F r = inv(run);
+        for (uint32_t i = i1; i-- > i0;) {
+            F t = CoordIO<F>::ld_plain(T + (size_t)i * CB);
+            CoordIO<F>::st(T + (size_t)i * CB, r * CoordIO<F>::ld_plain(pre2 + (size_t)i * CB));
+            r = r * t;
+        }
+    }
+}
+
+template <class F, bool L0>
+__global__ void __launch_bounds__(128, 4)
+k_pair_bwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off_in,
+           const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, const char* __restrict__ pre,
+           const char* __restrict__ Tinv, char* __restrict__ dst) {
+    constexpr int CB = CoordIO<F>::BYTES;
+    const uint32_t E = off_out[K];
+    const uint32_t nT = (E + m - 1) / m;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nT; t += gridDim.x * blockDim.x) {
+        const uint32_t e0 = t * m, e1 = (e0 + m < E) ? e0 + m : E;
+        PairCursor c;
+        cursor_seek(c, off_out, K, e1 - 1);
+        uint32_t ib = off_in[c.k], ie = off_in[c.k + 1];
+        F run = CoordIO<F>::ld_plain(Tinv + (size_t)t * CB);
+        for (uint32_t e = e1; e-- > e0;) {
+            while (e < c.lo) {
+                c.k--;
+                c.hi = c.lo;
+                c.lo = off_out[c.k];
+                ie = ib;
+                ib = off_in[c.k];
+            }
+            const uint32_t i0 = ib + 2 * (e - c.lo);
+            uint32_t s0, s1;
+            const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
+            F x0 = CoordIO<F>::ld_plain(p0), y0 = CoordIO<F>::ld_plain(p0 + CB);
+            if (s0) y0 = neg(y0);
+            F x3 = x0, y3 = y0;
+            if (i0 + 1 < ie) {
+                const char* p1 = pair_src<F, L0>(src, idx, i0 + 1, s1);
+                F x1 = CoordIO<F>::ld_plain(p1), y1 = CoordIO<F>::ld_plain(p1 + CB);
+                if (s1) y1 = neg(y1);
+                const bool inf0 = aff_is_identity(x0), inf1 = aff_is_identity(x1);
+                if (inf0) {
+                    x3 = x1;
+                    y3 = y1;
+                } else if (!inf1) {
+                    const bool same_x = (x0 == x1);
+                    if (same_x && y0 != y1) {
+                        aff_set_identity(x3, y3);   // P + (-P)
+                    } else {
+                        F d = same_x ? dbl(y0) : (x1 - x0);
+                        F dinv = run * CoordIO<F>::ld_plain(pre + (size_t)e * CB);
+                        run = run * d;
+                        F num;
+                        if (same_x) {
+                            F xx = sqr(x0);
+                            num = dbl(xx) + xx;
+                        } else {
+                            num = y1 - y0;
+                        }
+                        F lam = num * dinv;
+                        x3 = sqr(lam) - x0 - x1;
+                        y3 = lam * (x0 - x3) - y0;
+                    }
+                }
+            }
+            CoordIO<F>::st(dst + (size_t)e * (2 * CB), x3);
+            CoordIO<F>::st(dst + (size_t)e * (2 * CB) + CB, y3);
+        }
+    }
+}
+
+}  // namespace zkm

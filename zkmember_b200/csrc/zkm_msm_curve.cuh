@@ -5,6 +5,7 @@
 // src/models/short_weierstrass_jacobian.rs).
 #pragma once
 #include "zkm_msm.cuh"
+#include "zkm_msm_affine.cuh"
 
 namespace zkm {
 
@@ -83,7 +84,9 @@ k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx,
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
         const uint32_t task = order[t];
         const uint32_t s = tstart[task], len = tlen[task];
-        uint32_t id = idx[s];
+        // idx == nullptr: the lists are affine arrays written by the pairwise levels (position = entry,
+        // no sign, identity markers possible)
+        uint32_t id = idx ? idx[s] : s;
         const char* p = bases + (size_t)(id & 0x7fffffffu) * (2 * CB);
         F nx = CoordIO<F>::ld(p), ny = CoordIO<F>::ld(p + CB);
         uint32_t nsign = id >> 31;
@@ -92,7 +95,7 @@ k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx,
             F cx = nx, cy = ny;
             uint32_t csign = nsign;
             if (j + 1 < len) {
-                id = idx[s + j + 1];
+                id = idx ? idx[s + j + 1] : s + j + 1;
                 p = bases + (size_t)(id & 0x7fffffffu) * (2 * CB);
                 nx = CoordIO<F>::ld(p);
                 ny = CoordIO<F>::ld(p + CB);
@@ -100,7 +103,7 @@ k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx,
             }
             F my = neg(cy);
             if (csign) cy = my;
-            xyzz_madd(acc, cx, cy);
+            if (idx || !aff_is_identity(cx)) xyzz_madd(acc, cx, cy);
         }
         st_xyzz(out + task, acc);
     }
@@ -310,6 +313,46 @@ struct OpsImpl {
     static void accum_xyzz(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out) {
         ZKM_LAUNCH(k_accum_xyzz<F>, grid, 256, 0, s, (const XYZZ<F>*)items, tl, (XYZZ<F>*)out);
     }
+    // persistent grids: exactly the co-resident CTAs (or fewer when the level is small)
+    template <class K>
+    static unsigned pair_grid(K kernel, int block, unsigned sm_count, uint64_t threads_needed, int* cache) {
+        if (*cache == 0) {
+            ZKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(cache, kernel, block, 0));
+            if (*cache < 1) *cache = 1;
+        }
+        uint64_t need = (threads_needed + block - 1) / block;
+        uint64_t cap = (uint64_t)sm_count * (unsigned)*cache;
+        return (unsigned)(need < cap ? (need ? need : 1) : cap);
+    }
+    static void pair_fwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
+                         const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T) {
+        static int occ0 = 0, occ1 = 0;
+        if (level0) {
+            unsigned grid = pair_grid(k_pair_fwd<F, true>, 256, sm_count, nT_bound, &occ0);
+            ZKM_LAUNCH((k_pair_fwd<F, true>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T);
+        } else {
+            unsigned grid = pair_grid(k_pair_fwd<F, false>, 256, sm_count, nT_bound, &occ1);
+            ZKM_LAUNCH((k_pair_fwd<F, false>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T);
+        }
+    }
+    static void pair_inv(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
+                         uint32_t m2, void* T, void* pre2) {
+        static int occ = 0;
+        unsigned grid = pair_grid(k_inv_batch<F>, 128, sm_count, nU_bound, &occ);
+        ZKM_LAUNCH(k_inv_batch<F>, grid, 128, 0, s, off_out, K, m, m2, (char*)T, (char*)pre2);
+    }
+    static void pair_bwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
+                         const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre,
+                         const void* Tinv, void* dst) {
+        static int occ0 = 0, occ1 = 0;
+        if (level0) {
+            unsigned grid = pair_grid(k_pair_bwd<F, true>, 128, sm_count, nT_bound, &occ0);
+            ZKM_LAUNCH((k_pair_bwd<F, true>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst);
+        } else {
+            unsigned grid = pair_grid(k_pair_bwd<F, false>, 128, sm_count, nT_bound, &occ1);
+            ZKM_LAUNCH((k_pair_bwd<F, false>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst);
+        }
+    }
     static void reduce(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl,
                        void* contrib, void* wsum, uint64_t* d_out) {
         const uint32_t RW = (uint32_t)pl.RW;
@@ -357,6 +400,10 @@ struct OpsImpl {
         o.points_sum = points_sum;
         o.gen_progression = gen_progression;
         o.precompute = precompute;
+        o.pair_fwd = pair_fwd;
+        o.pair_inv = pair_inv;
+        o.pair_bwd = pair_bwd;
+        o.coord_bytes = CoordIO<F>::BYTES;
         return o;
     }
 };

@@ -300,6 +300,15 @@ __global__ void __launch_bounds__(256) k_qap_pointwise(uint32_t* __restrict__ a,
         st_fp<P>(a + i * P::N, fp_mul(fp_sub(fp_mul(x, y), w), z));
     }
 }
+// Fr::into_repr(): Montgomery -> canonical integer (the scalar format of multi_scalar_mul); device-resident
+// glue between the witness map (Montgomery coefficients h) and the h-query MSM.
+template <class P>
+__global__ void __launch_bounds__(256) k_fr_into_repr(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n) {
+    Fp<P> one_raw = Fp<P>::zero();
+    one_raw.l[0] = 1;   // the integer 1: a * 1 * R^-1 = canonical a
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        st_fp<P>(out + i * P::N, fp_mul(ld_fp_plain<P>(in + i * P::N), one_raw));
+}
 // out[0] = 1 / (g^(2^k) - 1)
 template <class P>
 __global__ void k_vanishing_inv(uint32_t* out, int k) {
@@ -318,6 +327,7 @@ static uint64_t table_key(uint64_t kind, int curve, int k, int inverse) {
 template <class P>
 static const uint32_t* get_twiddles(Context* c, int curve, int k, int inverse, cudaStream_t s) {
     if (k < 1) k = 1;
+    std::lock_guard<std::mutex> tw_lock(c->sh->tw_mu);
     uint64_t key = table_key(TW, curve, k, inverse);
     auto it = c->twiddles.find(key);
     if (it != c->twiddles.end()) return (const uint32_t*)it->second;
@@ -327,6 +337,7 @@ static const uint32_t* get_twiddles(Context* c, int curve, int k, int inverse, c
     c->twiddles[key] = p;
     unsigned blocks = (unsigned)((count + 255) / 256);
     ZKM_LAUNCH(k_gen_twiddles<P>, blocks, 256, 0, s, (uint32_t*)p, k, inverse, count);
+    ZKM_CUDA(cudaStreamSynchronize(s));  // first use only: other lanes' streams may read the table right away
     return (const uint32_t*)p;
 }
 
@@ -336,6 +347,7 @@ static void get_coset(Context* c, int curve, int k, int inverse, cudaStream_t s,
     int lb = k < 12 ? k : 12;
     *lo_bits = lb;
     uint64_t nlo = 1ull << lb, nhi = 1ull << (k - lb);
+    std::lock_guard<std::mutex> tw_lock(c->sh->tw_mu);
     uint64_t klo = table_key(COSET_LO, curve, k, inverse), khi = table_key(COSET_HI, curve, k, inverse);
     auto it = c->twiddles.find(klo);
     if (it != c->twiddles.end()) {
@@ -350,6 +362,7 @@ static void get_coset(Context* c, int curve, int k, int inverse, cudaStream_t s,
     c->twiddles[khi] = ph;
     unsigned blocks = (unsigned)((nlo + nhi + 255) / 256);
     ZKM_LAUNCH(k_gen_coset<P>, blocks, 256, 0, s, (uint32_t*)pl, (uint32_t*)ph, nlo, nhi, inverse, k);
+    ZKM_CUDA(cudaStreamSynchronize(s));
     *lo = (const uint32_t*)pl;
     *hi = (const uint32_t*)ph;
 }
@@ -441,6 +454,7 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
     memset(&a, 0, sizeof(a));
     if (inverse && !coset) {
         // size_inv lives in a cached 5-element device table of the domain constants
+        std::lock_guard<std::mutex> tw_lock(c->sh->tw_mu);
         uint64_t key = table_key(DOMAIN, curve, k, 0);
         auto it = c->twiddles.find(key);
         void* p;
@@ -448,6 +462,7 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
             ZKM_CUDA(cudaMalloc(&p, 5 * P::N * 4));
             c->twiddles[key] = p;
             ZKM_LAUNCH(k_domain_constants<P>, 1, 32, 0, s, (uint32_t*)p, k);
+            ZKM_CUDA(cudaStreamSynchronize(s));
         } else {
             p = it->second;
         }
@@ -487,21 +502,32 @@ static void witness_map_t(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, u
         ntt_run_t<P>(c, curve, vecs[v], tmp, log_n, 1, 0, s);   // ifft
         ntt_run_t<P>(c, curve, tmp, vecs[v], log_n, 0, 1, s);   // coset_fft
     }
-    uint64_t key = table_key(VANISH, curve, (int)log_n, 0);
-    auto it = c->twiddles.find(key);
     void* zinv;
-    if (it == c->twiddles.end()) {
-        ZKM_CUDA(cudaMalloc(&zinv, P::N * 4));
-        c->twiddles[key] = zinv;
-        ZKM_LAUNCH(k_vanishing_inv<P>, 1, 32, 0, s, (uint32_t*)zinv, (int)log_n);
-    } else {
-        zinv = it->second;
+    {
+        std::lock_guard<std::mutex> tw_lock(c->sh->tw_mu);
+        uint64_t key = table_key(VANISH, curve, (int)log_n, 0);
+        auto it = c->twiddles.find(key);
+        if (it == c->twiddles.end()) {
+            ZKM_CUDA(cudaMalloc(&zinv, P::N * 4));
+            c->twiddles[key] = zinv;
+            ZKM_LAUNCH(k_vanishing_inv<P>, 1, 32, 0, s, (uint32_t*)zinv, (int)log_n);
+            ZKM_CUDA(cudaStreamSynchronize(s));
+        } else {
+            zinv = it->second;
+        }
     }
     uint64_t blocks = (n + 255) / 256;
     uint64_t cap = (uint64_t)c->sm_count * 8;
     ZKM_LAUNCH(k_qap_pointwise<P>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, (uint32_t*)d_a, (const uint32_t*)d_b,
                (const uint32_t*)d_c, (const uint32_t*)zinv, n);
     ntt_run_t<P>(c, curve, d_a, d_h, log_n, 1, 1, s);           // coset_ifft
+}
+
+template <class P>
+static void fr_into_repr_t(Context* c, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t s) {
+    if (n == 0) return;
+    uint64_t blocks = (n + 255) / 256, cap = (uint64_t)c->sm_count * 8;
+    ZKM_LAUNCH(k_fr_into_repr<P>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, (const uint32_t*)d_in, (uint32_t*)d_out, n);
 }
 
 }  // namespace zkm

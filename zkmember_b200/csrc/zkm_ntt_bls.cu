@@ -7,6 +7,13 @@ void ntt_run_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint32_t log_
 void ntt_domain_constants_bn(Context* c, uint32_t* d, int log_n);
 void witness_map_bn(Context* c, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h, cudaStream_t s);
 
+void fr_into_repr_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t s);
+void fr_into_repr_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t s) {
+    if (curve == ZKM_CURVE_BLS12_381) fr_into_repr_t<Bls12_381_FrP>(c, d_in, d_out, n, s);
+    else if (curve == ZKM_CURVE_BN254) fr_into_repr_bn(c, d_in, d_out, n, s);
+    else ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+}
+
 void witness_map_run(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
                      cudaStream_t s) {
     if (curve == ZKM_CURVE_BLS12_381) witness_map_t<Bls12_381_FrP>(c, curve, d_a, d_b, d_c, log_n, d_h, s);
@@ -21,8 +28,7 @@ void ntt_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint3
     else ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
 }
 
-void ntt_domain_constants(int curve, uint32_t log_n, uint64_t* out5x4_host) {
-    Context* c = ctx();
+void ntt_domain_constants(Context* c, int curve, uint32_t log_n, uint64_t* out5x4_host) {
     if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
     int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
     if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
@@ -33,11 +39,9 @@ void ntt_domain_constants(int curve, uint32_t log_n, uint64_t* out5x4_host) {
     ZKM_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-void ntt_release(Context* c) {
-    for (auto& kv : c->twiddles) cudaFree(kv.second);
-    c->twiddles.clear();
-    c->ntt_a.release();
-    c->ntt_b.release();
+void ntt_release_tables(Shared* sh) {
+    for (auto& kv : sh->twiddles) cudaFree(kv.second);
+    sh->twiddles.clear();
 }
 
 }  // namespace zkm

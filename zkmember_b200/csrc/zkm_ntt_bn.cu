@@ -9,6 +9,9 @@ void ntt_run_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint32_t log_
 void witness_map_bn(Context* c, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h, cudaStream_t s) {
     witness_map_t<Bn254_FrP>(c, ZKM_CURVE_BN254, d_a, d_b, d_c, log_n, d_h, s);
 }
+void fr_into_repr_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t s) {
+    fr_into_repr_t<Bn254_FrP>(c, d_in, d_out, n, s);
+}
 void ntt_domain_constants_bn(Context* c, uint32_t* d, int log_n) {
     ZKM_LAUNCH(k_domain_constants<Bn254_FrP>, 1, 32, 0, c->stream, d, log_n);
 }
