@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--skip-ntt", action="store_true")
+    ap.add_argument("--skip-proxy", action="store_true", help="skip the Groth16 proof proxy leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -369,6 +370,31 @@ def main():
                "note": "device-resident, out of place; integer-pipe bound on B200, see DESIGN.md"}
         del x, y
 
+    # ---- third headline of BASELINE.json's metric: Groth16 proofs/s.  A zkMember-shaped PROXY (MSM + NTT
+    # work of create_proof at domain 2^16; tools/groth16_proxy.py) run on every GPU as an independent
+    # replica (batched proofs are distributed per GPU, no collective); the per-GPU rates are summed.
+    proxy = None
+    if not args.skip_proxy:
+        torch.cuda.synchronize()
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "40",
+               "--inflight", "2", "--device", str(local_rank)]
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            cmd.append("--cpu")
+        try:
+            env = dict(os.environ)
+            for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            outp = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            mine = json.loads(outp.stdout.strip().splitlines()[-1])
+        except Exception as e:  # noqa: BLE001
+            mine = {"error": repr(e)}
+        rates = torch.tensor([mine.get("proofs_per_s", 0.0)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(rates, op=dist.ReduceOp.SUM)
+        proxy = dict(mine)
+        proxy["proofs_per_s_all_gpus"] = float(rates[0])
+        proxy["replicas"] = world
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_baseline_run(1, 0, CPU_SAMPLE_LOG_N)
@@ -386,7 +412,7 @@ def main():
                        "result_ok": ok},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "msm_stage_ms": {"sort": acc[0], "affine_levels": acc[1], "tasks": acc[2], "accumulate_xyzz": acc[3], "fold": acc[4], "reduce": acc[5]},
-            "cpu_baseline": cpu, "ntt": ntt,
+            "cpu_baseline": cpu, "ntt": ntt, "groth16_proxy": proxy,
         }
         print(json.dumps(line))
     if world > 1:

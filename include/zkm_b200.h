@@ -76,6 +76,14 @@ int32_t zkm_bases_release(uint64_t handle);
 int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scalars, size_t n,
                            uint64_t* out_xy, uint8_t* out_inf);
 
+/* Replaces the non-hiding part of ark_poly_commit::kzg10::KZG10::commit (ark-poly-commit 0.3.0
+ * src/kzg10/mod.rs; reached from /root/reference/benches/marlin.rs:202,311 through MarlinKZG10::commit):
+ * skip_leading_zeros_and_convert_to_bigints + multi_scalar_mul(powers_of_g[z..], coeffs).  `handle` is a
+ * registration of powers_of_g, `coeffs` are the n polynomial coefficients as Montgomery Fr (HOST pointer,
+ * low degree first); the zero-skip, into_repr() and the MSM run on the device.  Returns the affine
+ * commitment.  The hiding term (a second, small MSM over powers_of_gamma_g) is a second call + one add. */
+int32_t zkm_kzg_commit(uint64_t handle, const uint64_t* coeffs, size_t n, uint64_t* out_xy, uint8_t* out_inf);
+
 /* ---- radix-2 NTT ------------------------------------------------------------------------------
  * Replaces ark_poly::Radix2EvaluationDomain::{fft_in_place, ifft_in_place, coset_fft_in_place,
  * coset_ifft_in_place} (ark-poly 0.3.0 src/domain/radix2/{mod,fft}.rs, src/domain/mod.rs) on the

@@ -380,3 +380,30 @@ def test_msm_affine_levels_random(zkm, curve, levels, kind):
         zkm.set_option("msm_affine_levels", -1)
         zkm.set_option("msm_window_bits", 0)
     _check_point(curve, 1, got, want_xy, want_inf)
+
+
+# ------------------------------------------------------------------------------- 8f row 3: KZG10 commit
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("precompute", [False, True])
+def test_kzg_commit_matches_oracle(zkm, curve, precompute):
+    """KZG10::commit (non-hiding part): leading-zero skip + into_repr + MSM over powers[z..]."""
+    from zkmember_b200.kzg import KZG10, Powers
+    fr = curve.fr
+    n = 1500
+    powers = capi.progression(curve.curve_id, 1, 5, 3, n)       # stand-in SRS (any G1 points)
+    pw = Powers(curve.name, powers, precompute=precompute)
+    fid = 1 if curve.curve_id == 0 else 3
+    try:
+        for deg, lead in ((n - 1, 0), (999, 7), (10, 11), (0, 0)):
+            coeffs = capi.random_field_elements(curve.curve_id, deg + 1, seed=deg + lead)
+            coeffs[:min(lead, deg + 1)] = 0
+            z = 0
+            while z < len(coeffs) and not coeffs[z].any():
+                z += 1
+            repr_ = np.stack([capi.field_op(fid, 4, coeffs[i]) for i in range(z, len(coeffs))]) if z < len(coeffs) \
+                else np.zeros((0, 4), dtype=np.uint64)
+            want_xy, want_inf = capi.msm(curve.curve_id, 1, powers[z:z + len(repr_)], repr_)
+            got = KZG10.commit(pw, coeffs)
+            _check_point(curve, 1, got, want_xy, want_inf)
+    finally:
+        pw.release()

@@ -295,6 +295,35 @@ int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scala
     });
 }
 
+int32_t zkm_kzg_commit(uint64_t handle, const uint64_t* coeffs, size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+    return guarded([&] {
+        LaneGuard lane;
+        Context* c = lane.c;
+        if (!out_xy || !out_inf || (n && !coeffs)) ZKM_FAIL(ZKM_ERR_ARG, "null pointer");
+        ZKM_CUDA(cudaSetDevice(c->device));
+        // skip_leading_zeros_and_convert_to_bigints: drop the zero coefficients at the low end, keep the offset
+        size_t z = 0;
+        while (z < n && (coeffs[4 * z] | coeffs[4 * z + 1] | coeffs[4 * z + 2] | coeffs[4 * z + 3]) == 0) z++;
+        const size_t m = n - z;
+        const BasesReg r = lookup(c, handle, z, m);
+        if (r.group != 1) ZKM_FAIL(ZKM_ERR_ARG, "KZG powers must be G1 bases");
+        const int W = coord_words(r.curve, r.group);
+        const size_t rec = 2 * (size_t)W * 8;
+        c->begin(c->stream);
+        uint64_t* d_scal = (uint64_t*)c->io_scalars.get((m ? m : 1) * 32);
+        uint64_t* d_out = (uint64_t*)c->io_out.get((2 * W + 1) * 8);
+        h2d(d_scal, coeffs + 4 * z, m * 32, c->stream);
+        fr_into_repr_run(c, r.curve, d_scal, d_scal, (uint64_t)m, c->stream);   // coeffs.into_repr()
+        msm_run(c, r.curve, r.group, (const char*)r.d_xy + z * rec, r.d_inf ? r.d_inf + z : nullptr, d_scal, m, d_out,
+                c->stream, &r, z);
+        uint64_t* h = (uint64_t*)c->pin_in.get((2 * W + 1) * 8);
+        ZKM_CUDA(cudaMemcpyAsync(h, d_out, (2 * W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        ZKM_CUDA(cudaStreamSynchronize(c->stream));
+        memcpy(out_xy, h, 2 * W * 8);
+        *out_inf = h[2 * W] ? 1 : 0;
+    });
+}
+
 int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n, uint64_t* d_out,
                                   void* stream) {
     return guarded([&] {

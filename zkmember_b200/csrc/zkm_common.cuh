@@ -160,7 +160,7 @@ struct Context {
     }
 };
 
-constexpr int ZKM_NUM_LANES = 6;
+constexpr int ZKM_NUM_LANES = 12;
 Context* acquire_lane();           // blocks until a lane is free; throws ZKM_ERR_NOT_INIT before zkm_init
 void release_lane(Context* c);
 struct LaneGuard {
