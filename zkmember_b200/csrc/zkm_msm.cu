@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
             } else {
                 nb = 64;  // flush: the rest of the buffer is zero extension
             }
-            while (nb >= pl.c && w < pl.W && (MODE == 0 || w <= w_only)) {
+            while (nb >= pl.c && w < pl.W && (MODE == 0 || w_only < 0 || w <= w_only)) {
                 uint32_t d = ((uint32_t)buf & mask) + carry;
                 buf >>= pl.c;
                 nb -= pl.c;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                     sign = 1;
                     carry = 1;
                 }
-                if (d != 0 && (MODE == 0 || w == w_only)) {
+                if (d != 0 && (MODE == 0 || w_only < 0 || w == w_only)) {
                     uint32_t key = (uint32_t)w * pl.key_stride + (d - 1);
                     if (MODE == 0) {
                         atomicAdd(&counts_or_cursor[key], 1u);
@@ -310,9 +310,15 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
                (uint32_t*)nullptr, flags);
     exclusive_scan(c, counts, off, K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(cursor, off, K * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    for (int w = 0; w < pl.W; w++)
-        ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w, cursor,
+    if (entries * sizeof(uint32_t) <= (96u << 20)) {
+        // the whole list array fits in L2: one launch scatters every window
+        ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, cursor,
                    idx, flags);
+    } else {
+        for (int w = 0; w < pl.W; w++)
+            ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w, cursor,
+                       idx, flags);
+    }
 
     mark(1);
     const unsigned kblocks = (K + 1 + 255) / 256;
