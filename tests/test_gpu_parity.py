@@ -407,3 +407,38 @@ def test_kzg_commit_matches_oracle(zkm, curve, precompute):
             _check_point(curve, 1, got, want_xy, want_inf)
     finally:
         pw.release()
+
+
+# ------------------------------------------------------------------------------- lanes: concurrent host threads
+def test_concurrent_calls_from_threads(zkm):
+    """Compute calls borrow independent lanes: MSMs (G1 + G2), NTTs and witness maps issued from several
+    host threads at once must all return the bytes of the serial run."""
+    from concurrent.futures import ThreadPoolExecutor
+    from zkmember_b200.groth16 import witness_map
+    curve = BLS12_381
+    n = 4096
+    b1 = capi.progression(0, 1, 3, 5, n)
+    b2 = capi.progression(0, 2, 3, 5, 512)
+    regs = [zkm.RegisteredBases("bls12_381", 1, b1), zkm.RegisteredBases("bls12_381", 2, b2)]
+    scal = [capi.random_scalars(0, n, seed=s, kind=k) for s, k in ((1, "uniform"), (2, "witness"), (3, "uniform"))]
+    x = capi.random_field_elements(0, 1 << 13, seed=9)
+    dom = zkm.Radix2EvaluationDomain("bls12_381", 13)
+    a, b, c = (capi.random_field_elements(0, 1 << 12, seed=s) for s in (4, 5, 6))
+    jobs = [
+        lambda: ("m0", regs[0].msm(scal[0]).to_bytes()),
+        lambda: ("m1", regs[0].msm(scal[1]).to_bytes()),
+        lambda: ("m2", regs[1].msm(scal[2][:512]).to_bytes()),
+        lambda: ("f", dom.fft(x).tobytes()),
+        lambda: ("ci", dom.coset_ifft(x).tobytes()),
+        lambda: ("w", witness_map(a, b, c).tobytes()),
+    ]
+    want = dict(j() for j in jobs)                      # serial reference
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        for _ in range(4):                                # several rounds of 12 concurrent calls
+            got = [f.result() for f in [ex.submit(j) for j in jobs + jobs]]
+            for k, v in got:
+                assert v == want[k], k
+    xy, inf = capi.msm(0, 1, b1, scal[0])
+    assert want["m0"] == xy.tobytes() + bytes([1 if inf else 0])
+    for r in regs:
+        r.release()

@@ -205,6 +205,22 @@ __device__ __forceinline__ Fp<P> ld_fp(const void* p) {
     }
     return r;
 }
+// Random gathers of whole base records: ask L2 for 64-byte fills instead of the default 128-byte lines
+// (a 96-byte record at a random 32-byte-aligned address otherwise drags in 192 bytes on average).
+template <class P>
+__device__ __forceinline__ Fp<P> ld_fp_gather(const void* p) {
+    Fp<P> r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < P::N / 4; i++) {
+        uint4 v;
+        asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(q + i));
+        r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
 template <class P>
 __device__ __forceinline__ Fp<P> ld_fp_plain(const void* p) {  // coherent load (data written earlier in the same kernel)
     Fp<P> r;
@@ -229,6 +245,7 @@ template <class P> struct CoordIO<Fp<P>> {
     static constexpr int BYTES = P::N * 4;
     static __device__ __forceinline__ Fp<P> ld(const void* p) { return ld_fp<P>(p); }
     static __device__ __forceinline__ Fp<P> ld_plain(const void* p) { return ld_fp_plain<P>(p); }
+    static __device__ __forceinline__ Fp<P> ld_gather(const void* p) { return ld_fp_gather<P>(p); }
     static __device__ __forceinline__ void st(void* p, const Fp<P>& a) { st_fp<P>(p, a); }
 };
 template <class P> struct CoordIO<Fp2<P>> {
@@ -237,6 +254,12 @@ template <class P> struct CoordIO<Fp2<P>> {
         Fp2<P> r;
         r.c0 = ld_fp<P>(p);
         r.c1 = ld_fp<P>(reinterpret_cast<const char*>(p) + P::N * 4);
+        return r;
+    }
+    static __device__ __forceinline__ Fp2<P> ld_gather(const void* p) {
+        Fp2<P> r;
+        r.c0 = ld_fp_gather<P>(p);
+        r.c1 = ld_fp_gather<P>(reinterpret_cast<const char*>(p) + P::N * 4);
         return r;
     }
     static __device__ __forceinline__ Fp2<P> ld_plain(const void* p) {

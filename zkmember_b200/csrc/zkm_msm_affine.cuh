@@ -99,12 +99,14 @@ k_pair_fwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const
                 uint32_t s0, s1;
                 const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
                 const char* p1 = pair_src<F, L0>(src, idx, i0 + 1, s1);
-                F x0 = CoordIO<F>::ld_plain(p0), x1 = CoordIO<F>::ld_plain(p1);
+                F x0 = L0 ? CoordIO<F>::ld_gather(p0) : CoordIO<F>::ld_plain(p0);
+                F x1 = L0 ? CoordIO<F>::ld_gather(p1) : CoordIO<F>::ld_plain(p1);
                 if (!aff_is_identity(x0) && !aff_is_identity(x1)) {
                     if (x0 != x1) {
                         run = run * (x1 - x0);
                     } else {
-                        F y0 = CoordIO<F>::ld_plain(p0 + CB), y1 = CoordIO<F>::ld_plain(p1 + CB);
+                        F y0 = L0 ? CoordIO<F>::ld_gather(p0 + CB) : CoordIO<F>::ld_plain(p0 + CB);
+                        F y1 = L0 ? CoordIO<F>::ld_gather(p1 + CB) : CoordIO<F>::ld_plain(p1 + CB);
                         if (s0) y0 = neg(y0);
                         if (s1) y1 = neg(y1);
                         if (y0 == y1) run = run * dbl(y0);
@@ -166,12 +168,14 @@ k_pair_bwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const
             const uint32_t i0 = ib + 2 * (e - c.lo);
             uint32_t s0, s1;
             const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
-            F x0 = CoordIO<F>::ld_plain(p0), y0 = CoordIO<F>::ld_plain(p0 + CB);
+            F x0 = L0 ? CoordIO<F>::ld_gather(p0) : CoordIO<F>::ld_plain(p0);
+            F y0 = L0 ? CoordIO<F>::ld_gather(p0 + CB) : CoordIO<F>::ld_plain(p0 + CB);
             if (s0) y0 = neg(y0);
             F x3 = x0, y3 = y0;
             if (i0 + 1 < ie) {
                 const char* p1 = pair_src<F, L0>(src, idx, i0 + 1, s1);
-                F x1 = CoordIO<F>::ld_plain(p1), y1 = CoordIO<F>::ld_plain(p1 + CB);
+                F x1 = L0 ? CoordIO<F>::ld_gather(p1) : CoordIO<F>::ld_plain(p1);
+                F y1 = L0 ? CoordIO<F>::ld_gather(p1 + CB) : CoordIO<F>::ld_plain(p1 + CB);
                 if (s1) y1 = neg(y1);
                 const bool inf0 = aff_is_identity(x0), inf1 = aff_is_identity(x1);
                 if (inf0) {

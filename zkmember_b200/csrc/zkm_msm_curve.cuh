@@ -88,7 +88,7 @@ k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx,
         // no sign, identity markers possible)
         uint32_t id = idx ? idx[s] : s;
         const char* p = bases + (size_t)(id & 0x7fffffffu) * (2 * CB);
-        F nx = CoordIO<F>::ld(p), ny = CoordIO<F>::ld(p + CB);
+        F nx = CoordIO<F>::ld_gather(p), ny = CoordIO<F>::ld_gather(p + CB);
         uint32_t nsign = id >> 31;
         XYZZ<F> acc = XYZZ<F>::identity();
         for (uint32_t j = 0; j < len; j++) {
@@ -97,8 +97,8 @@ k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx,
             if (j + 1 < len) {
                 id = idx ? idx[s + j + 1] : s + j + 1;
                 p = bases + (size_t)(id & 0x7fffffffu) * (2 * CB);
-                nx = CoordIO<F>::ld(p);
-                ny = CoordIO<F>::ld(p + CB);
+                nx = CoordIO<F>::ld_gather(p);
+                ny = CoordIO<F>::ld_gather(p + CB);
                 nsign = id >> 31;
             }
             F my = neg(cy);
@@ -129,8 +129,9 @@ k_accum_xyzz(const XYZZ<F>* __restrict__ items, const TaskList tl, XYZZ<F>* __re
 }
 
 // ---------------------------------------------------------------------------------- K5 reduction
-// The G1 kernels inline the group law at the few hot call sites of the reduction (registers instead
-// of local memory); G2 keeps the out-of-line copies (four times the code per formula).
+// The G1 kernels inline the group law at the few hot call sites of the reduction (registers instead of
+// local memory); G2 keeps the out-of-line copies: inlining them was measured (2^16 b_g2 MSM 8.9 -> 8.0 ms)
+// but costs 4 more minutes of ptxas time per G2 translation unit.
 template <class F> struct InlineLaw { static constexpr bool value = sizeof(F) <= 48; };
 template <class F>
 __device__ __forceinline__ void add_sel(XYZZ<F>& p, const XYZZ<F>& q) {
@@ -144,7 +145,7 @@ __device__ __forceinline__ void dbl_sel(XYZZ<F>& p) {
 // Thread (w, t) owns buckets b in [t*g, (t+1)*g) of window w:  sum_b (b+1) S_b = acc + lo * run with
 // run = sum S_b, acc = sum (b - lo + 1) S_b (running sums from the top), lo = t*g.
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_bucket_reduce(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
                 uint32_t W, uint32_t B, uint32_t g, XYZZ<F>* __restrict__ contrib) {
     const uint32_t per_w = B / g;
