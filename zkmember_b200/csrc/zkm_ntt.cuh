@@ -134,26 +134,50 @@ __device__ __forceinline__ uint32_t ntt_slot(uint32_t tau, uint32_t q, int pl) {
 }
 __device__ __forceinline__ uint32_t ntt_phys(uint32_t slot) { return slot ^ ((slot >> 3) & 7u); }
 
-// one DIF stage on q-bit BETA of the 8 register-resident elements
-template <class P, int R, int BETA>
-__device__ __forceinline__ void ntt_stage(Fp<P> (&x)[8], uint32_t tau, int pl, const uint32_t* tw_tile) {
-    const int g = pl + BETA;   // bit position of the butterfly distance inside the tile
-    const int t = R - 1 - g;   // DIF stage index
+// Register rotation q -> rotl3(q): after it, the bit the NEXT stage butterflies on sits in position 2,
+// so every stage runs the same four butterflies (i, i + 4).  One loop body of four Montgomery products
+// instead of twelve unrolled ones keeps the round inside the instruction cache.
+template <class P>
+__device__ __forceinline__ void ntt_rotate(Fp<P> (&x)[8]) {
+    Fp<P> t = x[4];
+    x[4] = x[2];
+    x[2] = x[1];
+    x[1] = t;
+    t = x[5];
+    x[5] = x[6];
+    x[6] = x[3];
+    x[3] = t;
+}
+
+// `ns` DIF stages (q-bits ns-1 .. 0 of the 8 register-resident elements, identity mapping x[q] <-> q on
+// entry and on exit)
+template <class P, int R>
+__device__ __forceinline__ void ntt_round(Fp<P> (&x)[8], uint32_t tau, int pl, int ns, const uint32_t* tw_tile) {
+    int rot = (3 - ns) % 3;  // rotations applied so far: register i holds original q = rotr3(i, rot)
+    if (rot >= 1) ntt_rotate<P>(x);
+    if (rot == 2) ntt_rotate<P>(x);
+#pragma unroll 1
+    for (int s = 0; s < ns; s++) {
+        const int beta = 2 - rot;      // original q-bit of this stage
+        const int g = pl + beta;       // bit position of the butterfly distance inside the tile
+        const int t = R - 1 - g;       // DIF stage index
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        if (q & (1 << BETA)) continue;
-        const int qb = q | (1 << BETA);
-        Fp<P> lo = x[q], hi = x[qb];
-        x[q] = fp_add(lo, hi);
-        Fp<P> d = fp_sub(lo, hi);
-        if (g == 0) {
-            x[qb] = d;  // w^0
-        } else {
-            uint32_t slot = ntt_slot(tau, q, pl);
-            uint32_t j = slot & ((1u << g) - 1u);
-            Fp<P> w = ld_fp<P>(tw_tile + ((size_t)j << t) * P::N);
-            x[qb] = fp_mul(d, w);
+        for (int i = 0; i < 4; i++) {
+            Fp<P> lo = x[i], hi = x[i + 4];
+            x[i] = fp_add(lo, hi);
+            Fp<P> d = fp_sub(lo, hi);
+            if (g == 0) {
+                x[i + 4] = d;  // w^0
+            } else {
+                const uint32_t q = (((uint32_t)i >> rot) | ((uint32_t)i << (3 - rot))) & 7u;
+                const uint32_t slot = ntt_slot(tau, q, pl);
+                const uint32_t j = slot & ((1u << g) - 1u);
+                Fp<P> w = ld_fp<P>(tw_tile + ((size_t)j << t) * P::N);
+                x[i + 4] = fp_mul(d, w);
+            }
         }
+        ntt_rotate<P>(x);
+        rot++;
     }
 }
 
@@ -221,9 +245,7 @@ __global__ void __launch_bounds__(NttCfg<R>::NT, NttCfg<R>::MINB) k_ntt_pass(con
                 }
             }
             if (active) {
-                if (ns == 3) ntt_stage<P, R, 2>(x, tau, pl, a.tw_tile);
-                if (ns >= 2) ntt_stage<P, R, 1>(x, tau, pl, a.tw_tile);
-                ntt_stage<P, R, 0>(x, tau, pl, a.tw_tile);
+                ntt_round<P, R>(x, tau, pl, ns, a.tw_tile);
             }
         }
         if (active) {
