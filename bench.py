@@ -362,12 +362,26 @@ def main():
         peaks = read_peaks()
         hbm = peaks["hbm_gbs"] if peaks and "hbm_gbs" in peaks else 6650.0
         gbs = 64.0 * n_ntt / (ms_ntt * 1e-3) / 1e9
+        ntt_traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            if CURVE_ID == 0 and LOG_N == 24:
+                ntt_traffic = tj.get("ntt_2p24_dram_bytes")
+        except Exception:
+            pass
+        # integer-pipe view of the same kernel: (log2 n / 2) Fr products per element x 136 wide MADs
+        ntt_mads = 0.5 * LOG_N * n_ntt * 136
+        ntt_gmads = ntt_mads / (ms_ntt * 1e-3) / 1e9
         ntt = {"metric": "Fr NTT 2^%d ms (%s)" % (LOG_N, CURVE_NAME), "ms": ms_ntt,
                "ntts_per_s_all_gpus": world * 1e3 / ms_ntt,
                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                            "algorithmic": "64 B/element (read once + write once)", "traffic": None},
-               "note": "device-resident, out of place; integer-pipe bound on B200, see DESIGN.md"}
+                            "algorithmic": "64 B/element (read once + write once)", "traffic": ntt_traffic},
+               "int_pipe": {"achieved": ntt_gmads, "peak": IMAD_PEAK_GMADS, "unit": "GMAD/s",
+                            "frac": ntt_gmads / IMAD_PEAK_GMADS,
+                            "algorithmic": "log2(n)/2 Fr products per element x 136 wide MADs"},
+               "note": "device-resident, out of place; integer-pipe bound on B200 (see DESIGN.md): the HBM fraction "
+                       "is reported as the contract asks, int_pipe is the binding roofline"}
         del x, y
 
     # ---- third headline of BASELINE.json's metric: Groth16 proofs/s.  A zkMember-shaped PROXY (MSM + NTT
