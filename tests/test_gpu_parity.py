@@ -225,11 +225,12 @@ def test_msm_rejects_non_canonical_scalar(zkm):
 
 
 @pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
-def test_msm_known_discrete_log_2p20(zkm, curve):
+@pytest.mark.parametrize("log_n,kind", [(20, "uniform"), (22, "uniform"), (22, "witness")])
+def test_msm_known_discrete_log_large(zkm, curve, log_n, kind):
     """Full-size property: with bases P_i = (a0 + i d) G generated on the device,
     sum s_i P_i == (sum s_i (a0 + i d) mod r) G, checked with exact big-int arithmetic."""
     import torch
-    n = 1 << 20
+    n = 1 << log_n      # 2^22 x 16 windows crosses the threshold of the batched-affine pairwise levels
     a0, d = 0x1234567, 0x89ABCDE
     W = 6 if curve.curve_id == 0 else 4
     dev = torch.device("cuda:0")
@@ -242,7 +243,7 @@ def test_msm_known_discrete_log_2p20(zkm, curve):
     head = d_bases[:64].cpu().numpy().view(np.uint64)
     assert np.array_equal(head, capi.progression(curve.curve_id, 1, a0, d, 64))
     reg = zkm.RegisteredBases.from_device(curve.name, 1, d_bases.data_ptr(), n)
-    scal = capi.random_scalars(curve.curve_id, n, seed=0x5EED0000 + 20)
+    scal = capi.random_scalars(curve.curve_id, n, seed=0x5EED0000 + log_n, kind=kind)
     got = reg.msm(scal)
     reg.release()
     r = curve.fr.modulus

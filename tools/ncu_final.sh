@@ -6,9 +6,9 @@ set -u
 TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
-python bench.py --steps 2 --warmup 3 --skip-cpu --skip-proxy > $OUT/bench_plain_$TAG.json 2> $OUT/bench_plain_$TAG.err || { echo "plain bench failed"; tail -5 $OUT/bench_plain_$TAG.err; exit 1; }
+python bench.py --steps 2 --warmup 3 --skip-cpu --skip-proxy --skip-precompute > $OUT/bench_plain_$TAG.json 2> $OUT/bench_plain_$TAG.err || { echo "plain bench failed"; tail -5 $OUT/bench_plain_$TAG.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_bench_$TAG.csv \
-    python bench.py --steps 2 --warmup 3 --skip-cpu --skip-proxy > $OUT/ncu_bench_$TAG.log 2>&1
+    python bench.py --steps 2 --warmup 3 --skip-cpu --skip-proxy --skip-precompute > $OUT/ncu_bench_$TAG.log 2>&1
 python tools/profile_target.py 24 > $OUT/pt_plain_$TAG.log 2>&1 || { echo "plain target failed"; exit 1; }
 cap() { # name regex skip count
   ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o /tmp/prof_$1 -f \

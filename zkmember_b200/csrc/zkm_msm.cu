@@ -175,7 +175,7 @@ static int auto_window_bits(int curve, size_t n, int precomputed) {
     if (n < 2) n = 2;
     double best = 1e300;
     int best_c = 4;
-    for (int c = 4; c <= 21; c++) {
+    for (int c = 4; c <= (precomputed ? 24 : 21); c++) {
         double W = windows_for(bits, c);
         double B = (double)(1u << (c - 1));
         // madd = 10 products per (point, window); per bucket: ~3 full adds (14 products) for the
