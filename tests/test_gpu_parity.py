@@ -443,3 +443,46 @@ def test_concurrent_calls_from_threads(zkm):
     assert want["m0"] == xy.tobytes() + bytes([1 if inf else 0])
     for r in regs:
         r.release()
+
+
+# ------------------------------------------------------------------------------- error behaviour of the C ABI
+def test_c_abi_error_codes(zkm):
+    """Errors surface as negative codes + message, never as aborts; valid calls keep working afterwards."""
+    L = zkm._lib.lib()
+    x = np.zeros((8, 4), dtype=np.uint64)
+    px = ctypes.c_void_p(x.ctypes.data)
+    assert L.zkm_ntt(7, px, 3, 0, 0) == -1 and b"curve" in L.zkm_last_error()          # ZKM_ERR_ARG
+    assert L.zkm_ntt(0, ctypes.c_void_p(0), 3, 0, 0) == -1
+    assert L.zkm_ntt(1, px, 29, 0, 0) == -4                                              # ZKM_ERR_DOMAIN (BN254: 28)
+    assert L.zkm_ntt(0, px, 33, 0, 0) == -4
+    out = np.zeros(12, dtype=np.uint64)
+    inf = np.zeros(1, dtype=np.uint8)
+    po, pi = ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(inf.ctypes.data)
+    assert L.zkm_msm_g1(5, px, ctypes.c_void_p(0), px, 1, po, pi) == -1
+    assert L.zkm_msm_g1(0, ctypes.c_void_p(0), ctypes.c_void_p(0), px, 1, po, pi) == -1  # null bases with n > 0
+    assert L.zkm_msm_g1(0, ctypes.c_void_p(0), ctypes.c_void_p(0), ctypes.c_void_p(0), 0, po, pi) == 0  # empty sum
+    assert inf[0] == 1 and not out[:6].any()                                              # identity: x = 0, y = 1 (Montgomery)
+    assert capi.limbs_to_ints(out[None, 6:])[0] == BLS12_381.fq.to_mont(1)
+    assert L.zkm_msm_registered(987654, 0, px, 1, po, pi) == -6                          # ZKM_ERR_HANDLE
+    assert L.zkm_bases_release(987654) == -6
+    assert L.zkm_set_option(b"no_such_option", 1) == -1
+    assert L.zkm_set_option(b"msm_window_bits", 99) == -1
+    assert L.zkm_init(0) == 0                                                             # idempotent
+    if L.zkm_device_count() > 1:
+        assert L.zkm_init(1) == -1                                                        # one process per GPU
+    # the library is still healthy
+    dom = zkm.Radix2EvaluationDomain("bls12_381", 3)
+    data = capi.random_field_elements(0, 8, seed=1)
+    assert np.array_equal(dom.fft(data), capi.ntt(0, data))
+
+
+def test_msm_truncates_to_shorter_input_like_upstream(zkm):
+    """multi_scalar_mul uses min(bases.len(), scalars.len()) pairs."""
+    bases = capi.progression(0, 1, 9, 4, 50)
+    scal = capi.random_scalars(0, 80, seed=3)
+    got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal)                 # 50 bases, 80 scalars
+    want_xy, want_inf = capi.msm(0, 1, bases, scal[:50])
+    _check_point(BLS12_381, 1, got, want_xy, want_inf)
+    got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal[:20])            # 50 bases, 20 scalars
+    want_xy, want_inf = capi.msm(0, 1, bases[:20], scal[:20])
+    _check_point(BLS12_381, 1, got, want_xy, want_inf)

@@ -466,6 +466,15 @@ int32_t zkm_set_option(const char* key, int64_t value) {
         } else if (!strcmp(key, "msm_affine_levels")) {
             if (value < -1 || value > 24) ZKM_FAIL(ZKM_ERR_ARG, "msm_affine_levels must be -1 (auto) or 0..24");
             c->opt.msm_affine_levels = (int)value;
+        } else if (!strcmp(key, "msm_pair_m")) {
+            if (value < 2 || value > 4096) ZKM_FAIL(ZKM_ERR_ARG, "msm_pair_m must be 2..4096");
+            c->opt.msm_pair_m = (int)value;
+        } else if (!strcmp(key, "msm_pair_m2")) {
+            if (value < 2 || value > 4096) ZKM_FAIL(ZKM_ERR_ARG, "msm_pair_m2 must be 2..4096");
+            c->opt.msm_pair_m2 = (int)value;
+        } else if (!strcmp(key, "msm_fold")) {
+            if (value != 0 && (value < 2 || value > 1024)) ZKM_FAIL(ZKM_ERR_ARG, "msm_fold must be 0 (auto) or 2..1024");
+            c->opt.msm_fold = (int)value;
         } else if (!strcmp(key, "msm_precompute")) {
             c->opt.msm_precompute = value ? 1 : 0;
         } else {

@@ -108,6 +108,8 @@ struct Options {
     int profile = 0;  // record CUDA events at the MSM stage boundaries
     int msm_precompute = 0;  // registrations made while set carry precomputed window multiples
     int msm_affine_levels = -1;  // batched-affine pairwise levels before the XYZZ tasks (-1 = automatic)
+    int msm_pair_m = 64, msm_pair_m2 = 32;  // outputs per thread / totals per inversion thread in the pair levels
+    int msm_fold = 0;            // fan-in of the XYZZ fold levels (0 = automatic: 4 for small MSMs, 16 for large)
 };
 
 // State shared by all lanes of the process (one process per GPU).
