@@ -435,8 +435,8 @@ def main():
     proxy = None
     if not args.skip_proxy:
         torch.cuda.synchronize()
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "40",
-               "--inflight", "2", "--device", str(local_rank)]
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "90",
+               "--inflight", "3", "--device", str(local_rank)]
         if rank == 0 and world == 1 and not args.skip_cpu:
             cmd.append("--cpu")
         try:

@@ -10,7 +10,7 @@ from oracle import capi
 zkm.init(0); L = _lib.lib()
 dev = torch.device("cuda:0"); st = torch.cuda.Stream(); torch.cuda.set_stream(st); sp = ctypes.c_void_p(st.cuda_stream)
 for group in (1, 2):
-    for lg in (15, 16, 18, 20):
+    for lg in (14, 15, 16, 17):
         if group == 2 and lg > 18: continue
         n = 1 << lg; W = 6 * group
         d_b = torch.empty((n, 2 * W), dtype=torch.int64, device=dev)
@@ -18,7 +18,7 @@ for group in (1, 2):
         torch.cuda.synchronize()
         d_s = torch.from_numpy(capi.random_scalars(0, n, seed=lg, kind="witness").view(np.int64)).to(dev)
         d_rec = torch.zeros(2 * W + 1, dtype=torch.int64, device=dev)
-        for c in (0, 9, 10, 11, 12, 13, 14, 15, 16):
+        for c in (0, 6, 7, 8, 9, 10):
             zkm.set_option("msm_window_bits", c); zkm.set_option("msm_precompute", 1)
             reg = zkm.RegisteredBases.from_device(0, group, d_b.data_ptr(), n)
             zkm.set_option("msm_precompute", 0)

@@ -162,7 +162,7 @@ struct Context {
     }
 };
 
-constexpr int ZKM_NUM_LANES = 12;
+constexpr int ZKM_NUM_LANES = 16;
 Context* acquire_lane();           // blocks until a lane is free; throws ZKM_ERR_NOT_INIT before zkm_init
 void release_lane(Context* c);
 struct LaneGuard {

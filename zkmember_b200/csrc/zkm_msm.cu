@@ -186,6 +186,16 @@ static int auto_window_bits(int curve, size_t n, int precomputed) {
             best_c = c;
         }
     }
+    if (precomputed && n < ((size_t)1 << 21)) {
+        // small registered MSMs are latency-bound: the serial chains of the single-bucket-set reduction grow
+        // with log2(B) = c - 1, so a smaller window wins although it adds entries (measured on B200, witness
+        // scalars: 2^16 G2 6.4 ms at c = 16 vs 4.0 ms at c = 9; 2^18 best at 12; 2^20 at 15-16)
+        int lg = 0;
+        while (((size_t)1 << (lg + 1)) <= n) lg++;
+        int c_lat = (3 * lg) / 2 - 15;
+        if (c_lat < 8) c_lat = 8;
+        if (c_lat < best_c) best_c = c_lat;
+    }
     return best_c;
 }
 
