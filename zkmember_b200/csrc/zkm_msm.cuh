@@ -63,7 +63,7 @@ struct CurveOps {
 // (and small enough that a small MSM still spreads over the SMs: the chain of 2 g additions is pure latency)
 inline uint32_t msm_reduce_group(uint32_t B, uint32_t W) {
     uint32_t g = 64;
-    while (g > 4 && (uint64_t)W * (B / g) < 16384) g >>= 1;
+    while (g > 4 && (uint64_t)W * (B / g) < 32768) g >>= 1;
     return g < B ? g : B;
 }
 // XYZZ records needed by CurveOps::reduce for `contrib`

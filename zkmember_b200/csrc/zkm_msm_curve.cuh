@@ -215,17 +215,72 @@ __device__ void write_result(uint64_t* out, const XYZZ<F>& p) {
     out[2 * CB / 8] = ok ? 0ull : 1ull;
 }
 
+// ---- lane-cooperative doubling for the Horner tail.  The window combine is a chain of c (W - 1) dependent
+// doublings on ONE point: pure latency (a dependent Montgomery product is ~1.8 k cycles on a lone warp).
+// Four lanes hold identical copies of the point; the nine products of dbl-2008-s-1 have dependency depth 3,
+// so every level is ONE product per lane on lane-selected operands (no divergence) followed by shuffles
+// that hand the results to all four lanes: 3 product latencies per doubling instead of 9.
+template <class P>
+__device__ __forceinline__ Fp<P> quad_bcast(const Fp<P>& v, int src) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.l[i] = __shfl_sync(0xfu, v.l[i], src, 4);
+    return r;
+}
+template <class P>
+__device__ __forceinline__ Fp2<P> quad_bcast(const Fp2<P>& v, int src) {
+    Fp2<P> r;
+    r.c0 = quad_bcast(v.c0, src);
+    r.c1 = quad_bcast(v.c1, src);
+    return r;
+}
+template <class P>
+__device__ __forceinline__ Fp<P> quad_sel(int q, const Fp<P>& a0, const Fp<P>& a1, const Fp<P>& a2, const Fp<P>& a3) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.l[i] = q == 0 ? a0.l[i] : (q == 1 ? a1.l[i] : (q == 2 ? a2.l[i] : a3.l[i]));
+    return r;
+}
+template <class P>
+__device__ __forceinline__ Fp2<P> quad_sel(int q, const Fp2<P>& a0, const Fp2<P>& a1, const Fp2<P>& a2, const Fp2<P>& a3) {
+    Fp2<P> r;
+    r.c0 = quad_sel(q, a0.c0, a1.c0, a2.c0, a3.c0);
+    r.c1 = quad_sel(q, a0.c1, a1.c1, a2.c1, a3.c1);
+    return r;
+}
+
+// p = 2 p; p is identical on the four lanes q = 0..3 on entry and on exit
+template <class F>
+__device__ __forceinline__ void xyzz_dbl_quad(XYZZ<F>& p, int q) {
+    if (p.is_identity()) return;
+    const F U = dbl(p.Y);
+    F r = quad_sel(q, U, p.X, U, U);
+    r = r * r;                                    // lane 0: V = U^2, lane 1: XX = X^2
+    const F V = quad_bcast(r, 0), XX = quad_bcast(r, 1);
+    const F M = dbl(XX) + XX;
+    r = quad_sel(q, U, p.X, p.ZZ, M) * quad_sel(q, V, V, V, M);   // W = U V | S = X V | ZZ' = ZZ V | M^2
+    const F Wv = quad_bcast(r, 0), S = quad_bcast(r, 1), ZZ3 = quad_bcast(r, 2), MM = quad_bcast(r, 3);
+    const F X3 = MM - dbl(S);
+    r = quad_sel(q, M, Wv, Wv, Wv) * quad_sel(q, S - X3, p.Y, p.ZZZ, p.ZZZ);   // M (S - X3) | W Y | ZZZ' = W ZZZ
+    const F T1 = quad_bcast(r, 0), T2 = quad_bcast(r, 1), ZZZ3 = quad_bcast(r, 2);
+    p.X = X3;
+    p.Y = T1 - T2;
+    p.ZZ = ZZ3;
+    p.ZZZ = ZZZ3;
+}
+
 template <class F>
 __global__ void k_msm_final(const XYZZ<F>* __restrict__ wsum, int W, int c, uint64_t* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x >= 4 || blockIdx.x != 0) return;
+    const int q = threadIdx.x;     // four cooperating lanes, identical state
     XYZZ<F> total = XYZZ<F>::identity();
     for (int w = W - 1; w >= 0; w--) {
         if (w != W - 1)
-            for (int k = 0; k < c; k++) dbl_sel(total);
+            for (int k = 0; k < c; k++) xyzz_dbl_quad(total, q);
         XYZZ<F> s = ld_xyzz(wsum + w);
         xyzz_add_ni(total, s);
     }
-    write_result<F>(out, total);
+    if (q == 0) write_result<F>(out, total);
 }
 
 template <class F>
