@@ -486,3 +486,20 @@ def test_msm_truncates_to_shorter_input_like_upstream(zkm):
     got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal[:20])            # 50 bases, 20 scalars
     want_xy, want_inf = capi.msm(0, 1, bases[:20], scal[:20])
     _check_point(BLS12_381, 1, got, want_xy, want_inf)
+
+
+def test_proving_key_msms_concurrent(zkm):
+    """The five MSMs of create_proof issued concurrently (zkmember_b200.groth16.ProvingKeyMSMs)."""
+    from zkmember_b200.groth16 import ProvingKeyMSMs
+    n = 1 << 10
+    q = {k: capi.progression(0, 2 if k == "b_g2" else 1, 3 + i, 2 + i, n) for i, k in enumerate(("h", "l", "a", "b_g1", "b_g2"))}
+    inf = {"b_g1": (np.arange(n) % 2).astype(np.uint8), "b_g2": (np.arange(n) % 3 == 0).astype(np.uint8)}
+    pk = ProvingKeyMSMs("bls12_381", q["h"], q["l"], q["a"], q["b_g1"], q["b_g2"], infinity=inf, precompute=True)
+    h = capi.random_scalars(0, n, 1)
+    w = capi.random_scalars(0, n, 2, "witness")
+    got = pk.prove_msms(h, w, w)
+    pk.release()
+    for name, key, sc, g in (("h_acc", "h", h, 1), ("l_acc", "l", w, 1), ("a_acc", "a", w, 1), ("b_g1_acc", "b_g1", w, 1),
+                             ("b_g2_acc", "b_g2", w, 2)):
+        xy, isinf = capi.msm(0, g, q[key], sc, inf.get(key))
+        _check_point(BLS12_381, g, got[name], xy, isinf)

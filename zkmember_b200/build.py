@@ -48,10 +48,10 @@ UNIT_HEADERS = {
     "zkm_ntt_bls.cu": ["zkm_ntt.cuh"],
     "zkm_ntt_bn.cu": ["zkm_ntt.cuh"],
     "zkm_msm.cu": ["zkm_msm.cuh"],
-    "zkm_msm_g1_bls.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh"],
-    "zkm_msm_g2_bls.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh"],
-    "zkm_msm_g1_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh"],
-    "zkm_msm_g2_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh"],
+    "zkm_msm_g1_bls.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
+    "zkm_msm_g2_bls.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
+    "zkm_msm_g1_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
+    "zkm_msm_g2_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
 }
 
 

@@ -408,7 +408,8 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, tpb[cur], K, L2, tpb[nxt], (uint32_t*)nullptr);
         exclusive_scan(c, tpb[nxt], tbase[nxt], K + 1, s);
         build_tasks(tbase[nxt], tbase[cur], tpb[cur], L2);
-        ops->accum_xyzz(grid_acc, s, part[cur], TaskList{tstart, tlen, order, tbase[nxt], K}, part[nxt]);
+        ops->accum_xyzz(grid_acc, s, part[cur], TaskList{tstart, tlen, order, tbase[nxt], K}, part[nxt],
+                        entries < ((size_t)4 << 20) ? 1 : 0);   // small MSM: latency-bound folds, four lanes per chain
         cur = nxt;
         maxseg = (maxseg + L2 - 1) / L2;
     }

@@ -38,7 +38,7 @@ struct CurveOps {
     // K4: out[task] = sum of the (sign-adjusted) affine bases named by idx[...]
     void (*accum_affine)(unsigned grid, cudaStream_t s, const void* bases, const uint32_t* idx, TaskList tl, void* out);
     // fold level: out[task] = sum of XYZZ items
-    void (*accum_xyzz)(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out);
+    void (*accum_xyzz)(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out, int quad);
     // K5: bucket sums (cnt[k] in {0,1}, item at off[k]) -> affine result record at d_out
     void (*reduce)(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl, void* contrib,
                    void* wsum, uint64_t* d_out);
@@ -69,7 +69,7 @@ inline uint32_t msm_reduce_group(uint32_t B, uint32_t W) {
 // XYZZ records needed by CurveOps::reduce for `contrib`
 inline size_t msm_contrib_records(int W, uint32_t B) {
     uint32_t per_w = B / msm_reduce_group(B, (uint32_t)W);
-    return (size_t)W * per_w + (size_t)W * ((per_w + 1023) / 1024) + 1;
+    return (size_t)W * per_w + (size_t)W * ((per_w + 255) / 256) + 1;   // second term: slice sums (quad path: 256 per slice)
 }
 
 const CurveOps* ops_g1_bls();

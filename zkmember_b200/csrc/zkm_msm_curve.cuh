@@ -6,6 +6,7 @@
 #pragma once
 #include "zkm_msm.cuh"
 #include "zkm_msm_affine.cuh"
+#include "zkm_msm_quad.cuh"
 
 namespace zkm {
 
@@ -215,72 +216,103 @@ __device__ void write_result(uint64_t* out, const XYZZ<F>& p) {
     out[2 * CB / 8] = ok ? 0ull : 1ull;
 }
 
-// ---- lane-cooperative doubling for the Horner tail.  The window combine is a chain of c (W - 1) dependent
-// doublings on ONE point: pure latency (a dependent Montgomery product is ~1.8 k cycles on a lone warp).
-// Four lanes hold identical copies of the point; the nine products of dbl-2008-s-1 have dependency depth 3,
-// so every level is ONE product per lane on lane-selected operands (no divergence) followed by shuffles
-// that hand the results to all four lanes: 3 product latencies per doubling instead of 9.
-template <class P>
-__device__ __forceinline__ Fp<P> quad_bcast(const Fp<P>& v, int src) {
-    Fp<P> r;
-#pragma unroll
-    for (int i = 0; i < P::N; i++) r.l[i] = __shfl_sync(0xfu, v.l[i], src, 4);
-    return r;
-}
-template <class P>
-__device__ __forceinline__ Fp2<P> quad_bcast(const Fp2<P>& v, int src) {
-    Fp2<P> r;
-    r.c0 = quad_bcast(v.c0, src);
-    r.c1 = quad_bcast(v.c1, src);
-    return r;
-}
-template <class P>
-__device__ __forceinline__ Fp<P> quad_sel(int q, const Fp<P>& a0, const Fp<P>& a1, const Fp<P>& a2, const Fp<P>& a3) {
-    Fp<P> r;
-#pragma unroll
-    for (int i = 0; i < P::N; i++) r.l[i] = q == 0 ? a0.l[i] : (q == 1 ? a1.l[i] : (q == 2 ? a2.l[i] : a3.l[i]));
-    return r;
-}
-template <class P>
-__device__ __forceinline__ Fp2<P> quad_sel(int q, const Fp2<P>& a0, const Fp2<P>& a1, const Fp2<P>& a2, const Fp2<P>& a3) {
-    Fp2<P> r;
-    r.c0 = quad_sel(q, a0.c0, a1.c0, a2.c0, a3.c0);
-    r.c1 = quad_sel(q, a0.c1, a1.c1, a2.c1, a3.c1);
-    return r;
-}
-
-// p = 2 p; p is identical on the four lanes q = 0..3 on entry and on exit
-template <class F>
-__device__ __forceinline__ void xyzz_dbl_quad(XYZZ<F>& p, int q) {
-    if (p.is_identity()) return;
-    const F U = dbl(p.Y);
-    F r = quad_sel(q, U, p.X, U, U);
-    r = r * r;                                    // lane 0: V = U^2, lane 1: XX = X^2
-    const F V = quad_bcast(r, 0), XX = quad_bcast(r, 1);
-    const F M = dbl(XX) + XX;
-    r = quad_sel(q, U, p.X, p.ZZ, M) * quad_sel(q, V, V, V, M);   // W = U V | S = X V | ZZ' = ZZ V | M^2
-    const F Wv = quad_bcast(r, 0), S = quad_bcast(r, 1), ZZ3 = quad_bcast(r, 2), MM = quad_bcast(r, 3);
-    const F X3 = MM - dbl(S);
-    r = quad_sel(q, M, Wv, Wv, Wv) * quad_sel(q, S - X3, p.Y, p.ZZZ, p.ZZZ);   // M (S - X3) | W Y | ZZZ' = W ZZZ
-    const F T1 = quad_bcast(r, 0), T2 = quad_bcast(r, 1), ZZZ3 = quad_bcast(r, 2);
-    p.X = X3;
-    p.Y = T1 - T2;
-    p.ZZ = ZZ3;
-    p.ZZZ = ZZZ3;
-}
-
+// ---- lane-cooperative group law for the serial tails (zkm_msm_quad.cuh) and the Horner combine
 template <class F>
 __global__ void k_msm_final(const XYZZ<F>* __restrict__ wsum, int W, int c, uint64_t* __restrict__ out) {
     if (threadIdx.x >= 4 || blockIdx.x != 0) return;
     const int q = threadIdx.x;     // four cooperating lanes, identical state
+    const uint32_t mask = 0xfu;
     XYZZ<F> total = XYZZ<F>::identity();
     for (int w = W - 1; w >= 0; w--) {
         if (w != W - 1)
-            for (int k = 0; k < c; k++) xyzz_dbl_quad(total, q);
+            for (int k = 0; k < c; k++) xyzz_dbl_quad_inl(total, q, mask);   // the 240-doubling chain: keep it in registers
         XYZZ<F> s = ld_xyzz(wsum + w);
-        xyzz_add_ni(total, s);
+        xyzz_add_quad(total, s, q, mask);
     }
     if (q == 0) write_result<F>(out, total);
+}
+
+// Quad versions of the tail kernels, used when the MSM is small (few thousand chains, all latency): one
+// chain per FOUR lanes.  Same arguments and results as the scalar kernels above.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bucket_reduce_quad(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+                     uint32_t W, uint32_t B, uint32_t g, XYZZ<F>* __restrict__ contrib) {
+    const uint32_t per_w = B / g;
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (gid >= W * per_w) return;
+    const int q = threadIdx.x & 3;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    const uint32_t w = gid / per_w, t = gid % per_w;
+    const uint32_t lo = t * g;
+    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+    for (uint32_t b = lo + g; b-- > lo;) {
+        const uint32_t k = w * B + b;
+        if (cnt[k]) {
+            XYZZ<F> S = ld_xyzz(items + off[k]);
+            xyzz_add_quad(run, S, q, mask);
+        }
+        xyzz_add_quad(acc, run, q, mask);
+    }
+    if (lo != 0 && !run.is_identity()) {
+        XYZZ<F> r = XYZZ<F>::identity();
+        for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+            xyzz_dbl_quad(r, q, mask);
+            if ((lo >> bit) & 1) xyzz_add_quad(r, run, q, mask);
+        }
+        xyzz_add_quad(acc, r, q, mask);
+    }
+    if (q == 0) st_xyzz(contrib + gid, acc);
+}
+
+// block = 128 threads = 32 quads
+template <class F>
+__global__ void __launch_bounds__(128) k_window_sum_quad(const XYZZ<F>* __restrict__ in, uint32_t per_w, uint32_t chunk,
+                                                         uint32_t nslices, XYZZ<F>* __restrict__ out) {
+    __shared__ XYZZ<F> sh[32];
+    const uint32_t w = blockIdx.x / nslices, slice = blockIdx.x % nslices;
+    const uint32_t begin = slice * chunk;
+    const uint32_t end = begin + chunk < per_w ? begin + chunk : per_w;
+    const int q = threadIdx.x & 3;
+    const uint32_t quad = threadIdx.x >> 2;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t t = begin + quad; t < end; t += 32) {
+        XYZZ<F> v = ld_xyzz(in + (size_t)w * per_w + t);
+        xyzz_add_quad(acc, v, q, mask);
+    }
+    if (q == 0) sh[quad] = acc;
+    __syncthreads();
+    for (uint32_t s = 16; s > 0; s >>= 1) {
+        if (quad < s) {
+            XYZZ<F> a = sh[quad], b = sh[quad + s];
+            xyzz_add_quad(a, b, q, mask);
+            if (q == 0) sh[quad] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(out + blockIdx.x, sh[0]);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_accum_xyzz_quad(const XYZZ<F>* __restrict__ items, const TaskList tl, XYZZ<F>* __restrict__ out) {
+    const uint32_t* __restrict__ tstart = tl.tstart;
+    const uint32_t* __restrict__ tlen = tl.tlen;
+    const uint32_t* __restrict__ order = tl.order;
+    const uint32_t T = tl.tbase[tl.K];
+    const int q = threadIdx.x & 3;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; t < T; t += (gridDim.x * blockDim.x) >> 2) {
+        const uint32_t task = order[t];
+        const uint32_t s = tstart[task], len = tlen[task];
+        XYZZ<F> acc = ld_xyzz(items + s);
+        for (uint32_t j = 1; j < len; j++) {
+            XYZZ<F> v = ld_xyzz(items + s + j);
+            xyzz_add_quad(acc, v, q, mask);
+        }
+        if (q == 0) st_xyzz(out + task, acc);
+    }
 }
 
 template <class F>
@@ -366,8 +398,9 @@ struct OpsImpl {
     static void accum_affine(unsigned grid, cudaStream_t s, const void* bases, const uint32_t* idx, TaskList tl, void* out) {
         ZKM_LAUNCH(k_accum_affine<F>, grid, 256, 0, s, (const char*)bases, idx, tl, (XYZZ<F>*)out);
     }
-    static void accum_xyzz(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out) {
-        ZKM_LAUNCH(k_accum_xyzz<F>, grid, 256, 0, s, (const XYZZ<F>*)items, tl, (XYZZ<F>*)out);
+    static void accum_xyzz(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out, int quad) {
+        if (quad) ZKM_LAUNCH(k_accum_xyzz_quad<F>, grid * 2, 128, 0, s, (const XYZZ<F>*)items, tl, (XYZZ<F>*)out);
+        else ZKM_LAUNCH(k_accum_xyzz<F>, grid, 256, 0, s, (const XYZZ<F>*)items, tl, (XYZZ<F>*)out);
     }
     // persistent grids: exactly the co-resident CTAs (or fewer when the level is small)
     template <class K>
@@ -414,18 +447,34 @@ struct OpsImpl {
         const uint32_t RW = (uint32_t)pl.RW;
         uint32_t g = msm_reduce_group(pl.B, RW);
         uint32_t per_w = pl.B / g;
-        unsigned rblocks = (RW * per_w + 127) / 128;
-        ZKM_LAUNCH(k_bucket_reduce<F>, rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, RW, pl.B, g,
-                   (XYZZ<F>*)contrib);
-        // two-step sum of the per-slice contributions of every window: per_w -> nslices -> 1
+        // small reductions are chains of dependent additions: run them four lanes per chain
+        const bool quad = (uint64_t)RW * per_w <= 16384;
         XYZZ<F>* stage = (XYZZ<F>*)contrib + (size_t)RW * per_w;
-        uint32_t nslices = (per_w + 1023) / 1024;
-        if (nslices > 1) {
-            uint32_t chunk = (per_w + nslices - 1) / nslices;
-            ZKM_LAUNCH(k_window_sum<F>, RW * nslices, 64, 0, s, (const XYZZ<F>*)contrib, per_w, chunk, nslices, stage);
-            ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)stage, nslices, nslices, 1u, (XYZZ<F>*)wsum);
+        if (quad) {
+            unsigned rblocks = (RW * per_w * 4 + 127) / 128;
+            ZKM_LAUNCH(k_bucket_reduce_quad<F>, rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, RW, pl.B, g,
+                       (XYZZ<F>*)contrib);
+            uint32_t nslices = (per_w + 255) / 256;
+            if (nslices > 1) {
+                uint32_t chunk = (per_w + nslices - 1) / nslices;
+                ZKM_LAUNCH(k_window_sum_quad<F>, RW * nslices, 128, 0, s, (const XYZZ<F>*)contrib, per_w, chunk, nslices, stage);
+                ZKM_LAUNCH(k_window_sum_quad<F>, RW, 128, 0, s, (const XYZZ<F>*)stage, nslices, nslices, 1u, (XYZZ<F>*)wsum);
+            } else {
+                ZKM_LAUNCH(k_window_sum_quad<F>, RW, 128, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u, (XYZZ<F>*)wsum);
+            }
         } else {
-            ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u, (XYZZ<F>*)wsum);
+            unsigned rblocks = (RW * per_w + 127) / 128;
+            ZKM_LAUNCH(k_bucket_reduce<F>, rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, RW, pl.B, g,
+                       (XYZZ<F>*)contrib);
+            // two-step sum of the per-slice contributions of every window: per_w -> nslices -> 1
+            uint32_t nslices = (per_w + 1023) / 1024;
+            if (nslices > 1) {
+                uint32_t chunk = (per_w + nslices - 1) / nslices;
+                ZKM_LAUNCH(k_window_sum<F>, RW * nslices, 64, 0, s, (const XYZZ<F>*)contrib, per_w, chunk, nslices, stage);
+                ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)stage, nslices, nslices, 1u, (XYZZ<F>*)wsum);
+            } else {
+                ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u, (XYZZ<F>*)wsum);
+            }
         }
         ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.RW, pl.c, d_out);
     }
