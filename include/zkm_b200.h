@@ -127,6 +127,13 @@ int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uin
  * Synchronises once internally (bucket-occupancy read-back that sizes the reduction tree). */
 int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n,
                                   uint64_t* d_out, void* stream);
+/* `count` independent MSMs over registered bases issued concurrently (one internal host thread, lane and
+ * stream per item), ordered after the current point of `stream` and joined back into it: the five MSMs of
+ * ark_groth16::create_proof (src/prover.rs) in one call, with the G2 MSM overlapping the G1 ones.
+ * Arrays of `count` entries; d_scalars[i] / d_outs[i] are DEVICE pointers as in zkm_msm_registered_device. */
+int32_t zkm_msm_batch_registered_device(int32_t count, const uint64_t* handles, const size_t* offsets,
+                                        const uint64_t* const* d_scalars, const size_t* n, uint64_t* const* d_outs,
+                                        void* stream);
 /* Adopt (copy) bases that already live in device memory. */
 int32_t zkm_bases_register_device(int32_t curve, int32_t group, const uint64_t* d_bases_xy,
                                   const uint8_t* d_infinity, size_t n, uint64_t* handle_out);

@@ -503,3 +503,26 @@ def test_proving_key_msms_concurrent(zkm):
                              ("b_g2_acc", "b_g2", w, 2)):
         xy, isinf = capi.msm(0, g, q[key], sc, inf.get(key))
         _check_point(BLS12_381, g, got[name], xy, isinf)
+
+
+def test_msm_batch_registered_device(zkm):
+    """zkm_msm_batch_registered_device: five concurrent MSMs in one call == five separate calls."""
+    import torch
+    from zkmember_b200.msm import msm_batch_device
+    n = 2000
+    regs, outs, want = [], [], []
+    scal = capi.random_scalars(0, n, 5, "witness")
+    d_s = torch.from_numpy(scal.view(np.int64)).cuda()
+    for i, g in enumerate((1, 1, 2, 1, 1)):
+        b = capi.progression(0, g, 7 + i, 3, n)
+        regs.append(zkm.RegisteredBases("bls12_381", g, b))
+        outs.append(torch.zeros(12 * g + 1, dtype=torch.int64, device="cuda"))
+        want.append(capi.msm(0, g, b, scal))
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        msm_batch_device([(regs[i], d_s.data_ptr(), n, outs[i].data_ptr()) for i in range(5)], stream=st.cuda_stream)
+        st.synchronize()
+    for i in range(5):
+        r = outs[i].cpu().numpy().view(np.uint64)
+        assert bool(r[-1]) == want[i][1] and np.array_equal(r[:-1], want[i][0]), i
+        regs[i].release()

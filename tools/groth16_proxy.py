@@ -37,6 +37,7 @@ ap.add_argument("--proofs", type=int, default=40)
 ap.add_argument("--inflight", type=int, default=1)
 ap.add_argument("--no-precompute", action="store_true")
 ap.add_argument("--serial", action="store_true", help="run the five MSMs of a proof one after another on one stream")
+ap.add_argument("--python-threads", action="store_true", help="issue the MSMs from five Python threads instead of one zkm_msm_batch_registered_device call")
 ap.add_argument("--cpu", action="store_true", help="check against / time the CPU restatement of the same work (1 proof)")
 ap.add_argument("--curve", default="bls12_381")
 ap.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")))
@@ -120,6 +121,14 @@ class Pipeline:
             if args.serial:
                 for k in KEYS:
                     self._msm(k, st.cuda_stream)
+            elif not args.python_threads:
+                # one C call: the library runs the five MSMs on five lanes / host threads of its own
+                from zkmember_b200.msm import msm_batch_device
+                src = {"h": (self.d_h.data_ptr(), sizes["h"]), "l": (self.d_full.data_ptr() + 32 * (n - sizes["l"]), sizes["l"]),
+                       "a": (self.d_full.data_ptr(), sizes["a"]), "b_g1": (self.d_full.data_ptr(), sizes["b_g1"]),
+                       "b_g2": (self.d_full.data_ptr(), sizes["b_g2"])}
+                msm_batch_device([(regs[k], src[k][0], src[k][1], self.recs[k].data_ptr()) for k in ("b_g2", "h", "l", "a", "b_g1")],
+                                 stream=st.cuda_stream)
             else:
                 ev_h = torch.cuda.Event()
                 ev_h.record(st)

@@ -27,7 +27,7 @@ SYMBOLS = [
     "zkm_msm_g1", "zkm_msm_g2", "zkm_bases_register", "zkm_bases_release", "zkm_msm_registered",
     "zkm_ntt", "zkm_domain_constants", "zkm_ntt_device", "zkm_msm_registered_device",
     "zkm_bases_register_device", "zkm_points_sum_device", "zkm_set_option", "zkm_launch_count",
-    "zkm_msm_window_bits", "zkm_testgen_progression_device", "zkm_profile_last_msm", "zkm_witness_map", "zkm_witness_map_device", "zkm_fr_into_repr_device", "zkm_kzg_commit",
+    "zkm_msm_window_bits", "zkm_testgen_progression_device", "zkm_profile_last_msm", "zkm_witness_map", "zkm_witness_map_device", "zkm_fr_into_repr_device", "zkm_kzg_commit", "zkm_msm_batch_registered_device",
 ]
 
 
@@ -75,6 +75,8 @@ def load():
     L.zkm_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     L.zkm_profile_last_msm.argtypes = [ctypes.c_void_p]
     L.zkm_fr_into_repr_device.argtypes = [i32, u64p, u64p, sz, vp]
+    L.zkm_msm_batch_registered_device.argtypes = [i32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p, vp]
     L.zkm_kzg_commit.argtypes = [u64, u64p, sz, u64p, u8p]
     L.zkm_witness_map.argtypes = [i32, u64p, u64p, u64p, u32, u64p]
     L.zkm_witness_map_device.argtypes = [i32, u64p, u64p, u64p, u32, u64p, vp]

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <thread>
+
 #include "zkm_common.cuh"
 
 namespace zkm {
@@ -39,6 +41,13 @@ Context* acquire_lane() {
         }
         g_lane_cv.wait(lk);
     }
+}
+
+int busy_lane_count() {
+    std::lock_guard<std::mutex> lk(g_lane_mu);
+    int n = 0;
+    for (Context* c : g_lanes) n += c->busy ? 1 : 0;
+    return n;
 }
 
 void release_lane(Context* c) {
@@ -196,6 +205,7 @@ void zkm_shutdown(void) {
         for (auto& e : c->pev)
             if (e) cudaEventDestroy(e);
         if (c->done_ev) cudaEventDestroy(c->done_ev);
+        if (c->sync_ev) cudaEventDestroy(c->sync_ev);
         cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
         delete c;
@@ -338,6 +348,63 @@ int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t
         msm_run(c, r.curve, r.group, (const char*)r.d_xy + offset * rec, r.d_inf ? r.d_inf + offset : nullptr, d_scalars, n,
                 d_out, s, &r, offset);
         c->end(s);
+    });
+}
+
+// `count` MSMs over registered bases issued CONCURRENTLY: one host thread + one lane + the lane's own
+// stream per item, all ordered after the current point of `stream` and joined back into it.  This is the
+// create_proof pattern (four G1 MSMs and the G2 one, ark-groth16 0.3.0 src/prover.rs): upstream runs them
+// back to back; here the G2 MSM and the serial tails of the G1 ones overlap.
+int32_t zkm_msm_batch_registered_device(int32_t count, const uint64_t* handles, const size_t* offsets,
+                                        const uint64_t* const* d_scalars, const size_t* n, uint64_t* const* d_outs,
+                                        void* stream) {
+    return guarded([&] {
+        if (count < 0 || count > ZKM_NUM_LANES - 2) ZKM_FAIL(ZKM_ERR_ARG, "count must be 0..%d", ZKM_NUM_LANES - 2);
+        if (count && (!handles || !offsets || !d_scalars || !n || !d_outs)) ZKM_FAIL(ZKM_ERR_ARG, "null argument array");
+        Context* c0 = ctx();
+        ZKM_CUDA(cudaSetDevice(c0->device));
+        cudaStream_t caller = stream ? (cudaStream_t)stream : c0->stream;
+        cudaEvent_t ev_in;
+        ZKM_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        ZKM_CUDA(cudaEventRecord(ev_in, caller));
+        std::vector<int32_t> rc((size_t)count, ZKM_OK);
+        std::vector<std::string> msg((size_t)count);
+        std::vector<cudaEvent_t> ev_out((size_t)count, nullptr);
+        std::vector<std::thread> th;
+        for (int i = 0; i < count; i++) {
+            th.emplace_back([&, i] {
+                rc[i] = guarded([&] {
+                    LaneGuard lane;
+                    Context* c = lane.c;
+                    ZKM_CUDA(cudaSetDevice(c->device));
+                    const BasesReg r = lookup(c, handles[i], offsets[i], n[i]);
+                    const size_t rec = 2 * (size_t)coord_words(r.curve, r.group) * 8;
+                    cudaStream_t s = c->stream;
+                    c->begin(s);
+                    ZKM_CUDA(cudaStreamWaitEvent(s, ev_in, 0));
+                    msm_run(c, r.curve, r.group, (const char*)r.d_xy + offsets[i] * rec, r.d_inf ? r.d_inf + offsets[i] : nullptr,
+                            d_scalars[i], n[i], d_outs[i], s, &r, offsets[i]);
+                    c->end(s);
+                    ZKM_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+                    ZKM_CUDA(cudaEventRecord(ev_out[i], s));
+                });
+                if (rc[i] != ZKM_OK) msg[i] = zkm_last_error();
+            });
+        }
+        for (auto& t : th) t.join();
+        int32_t first = ZKM_OK;
+        for (int i = 0; i < count; i++) {
+            if (ev_out[i]) {
+                cudaStreamWaitEvent(caller, ev_out[i], 0);
+                cudaEventDestroy(ev_out[i]);
+            }
+            if (rc[i] != ZKM_OK && first == ZKM_OK) {
+                first = rc[i];
+                set_error("item %d: %s", i, msg[i].c_str());
+            }
+        }
+        cudaEventDestroy(ev_in);
+        if (first != ZKM_OK) throw ZkmError{first};
     });
 }
 

@@ -153,6 +153,7 @@ struct Context {
     // The lane's workspaces may still be in use by kernels enqueued on the stream of its previous borrower:
     // every call orders itself after `done_ev` and re-records it when it has enqueued its work.
     cudaEvent_t done_ev = nullptr;
+    cudaEvent_t sync_ev = nullptr;   // blocking-sync event for host waits while many lanes are busy
     void begin(cudaStream_t s) {
         if (done_ev) ZKM_CUDA(cudaStreamWaitEvent(s, done_ev, 0));
     }
@@ -165,6 +166,7 @@ struct Context {
 constexpr int ZKM_NUM_LANES = 16;
 Context* acquire_lane();           // blocks until a lane is free; throws ZKM_ERR_NOT_INIT before zkm_init
 void release_lane(Context* c);
+int busy_lane_count();
 struct LaneGuard {
     Context* c;
     LaneGuard() : c(acquire_lane()) {}

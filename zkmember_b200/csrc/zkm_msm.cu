@@ -382,7 +382,16 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, cur_cnt, K, L1, tpb[0], flags);
     exclusive_scan(c, tpb[0], tbase[0], K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(h_flags, flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    ZKM_CUDA(cudaStreamSynchronize(s));  // the one host sync: largest bucket -> depth of the fold tree
+    // the one host sync: largest bucket -> depth of the fold tree.  A spinning wait is the fastest when few
+    // calls are in flight; with many concurrent lanes (batched proofs) the spinning host threads starve each
+    // other, so they block on an event instead.
+    if (busy_lane_count() > 6) {
+        if (!c->sync_ev) ZKM_CUDA(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+        ZKM_CUDA(cudaEventRecord(c->sync_ev, s));
+        ZKM_CUDA(cudaEventSynchronize(c->sync_ev));
+    } else {
+        ZKM_CUDA(cudaStreamSynchronize(s));
+    }
     if (h_flags[1])
         ZKM_FAIL(ZKM_ERR_SCALAR_RANGE, "a scalar has bits at or above bit %d (not a canonical Fr)", pl.scalar_bits + 1);
     const uint32_t maxcnt = h_flags[0];

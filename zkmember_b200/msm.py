@@ -135,3 +135,18 @@ class VariableBaseMSM:
 
 def msm_window_bits(curve, group: int, n: int) -> int:
     return int(_lib.load().zkm_msm_window_bits(_curve_id(curve), group, n))
+
+
+def msm_batch_device(items, stream: int = 0):
+    """Concurrent MSMs over registered bases, device resident (the create_proof pattern).
+    items: iterable of (RegisteredBases, d_scalars_ptr, n, d_out_ptr[, offset])."""
+    items = list(items)
+    k = len(items)
+    handles = (ctypes.c_uint64 * k)(*[it[0].handle for it in items])
+    offsets = (ctypes.c_size_t * k)(*[(it[4] if len(it) > 4 else 0) for it in items])
+    scal = (ctypes.c_void_p * k)(*[it[1] for it in items])
+    ns = (ctypes.c_size_t * k)(*[it[2] for it in items])
+    outs = (ctypes.c_void_p * k)(*[it[3] for it in items])
+    _lib.check(_lib.lib().zkm_msm_batch_registered_device(k, ctypes.cast(handles, ctypes.c_void_p), ctypes.cast(offsets, ctypes.c_void_p),
+                                                          ctypes.cast(scal, ctypes.c_void_p), ctypes.cast(ns, ctypes.c_void_p),
+                                                          ctypes.cast(outs, ctypes.c_void_p), ctypes.c_void_p(stream)))
