@@ -1,0 +1,119 @@
+// C++ host-layer parity test: drives include/zkm_b200.hpp (the compiled-language mirror of the arkworks
+// interfaces) over known-answer vectors handed in as text lines by tests/test_host_cpp.py:
+//   ntt <curve> <log_n> <inverse> <coset> <hex input> <hex output>
+//   msm <curve> <group> <n> <hex bases> <hex infinity flags> <hex scalars> <hex result> <result infinity>
+//   wmap <curve> <log_n> <hex a> <hex b> <hex c> <hex h>
+// Byte equality is the bar.  Exit code 0 = all vectors match.
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "../../include/zkm_b200.hpp"
+
+static std::vector<uint8_t> unhex(const std::string& s) {
+    std::vector<uint8_t> out;
+    if (s == "-") return out;
+    out.reserve(s.size() / 2);
+    auto v = [](char c) { return c <= '9' ? c - '0' : (c | 32) - 'a' + 10; };
+    for (size_t i = 0; i + 1 < s.size(); i += 2) out.push_back((uint8_t)(v(s[i]) * 16 + v(s[i + 1])));
+    return out;
+}
+
+template <class Curve>
+static bool run_ntt(int log_n, int inverse, int coset, const std::vector<uint8_t>& in, const std::vector<uint8_t>& want) {
+    typedef typename Curve::Fr F;
+    auto dom = zkm::Radix2EvaluationDomain<Curve>::new_(size_t(1) << log_n);
+    if (!dom) return false;
+    std::vector<F> v(in.size() / sizeof(F));
+    std::memcpy(v.data(), in.data(), in.size());
+    std::vector<F> r = inverse ? (coset ? dom->coset_ifft(v) : dom->ifft(v)) : (coset ? dom->coset_fft(v) : dom->fft(v));
+    return r.size() * sizeof(F) == want.size() && std::memcmp(r.data(), want.data(), want.size()) == 0;
+}
+
+template <class Curve, int GROUP>
+static bool run_msm(size_t n, const std::vector<uint8_t>& bases, const std::vector<uint8_t>& inf, const std::vector<uint8_t>& scal,
+                    const std::vector<uint8_t>& want, int want_inf) {
+    typedef zkm::GroupAffine<Curve, GROUP> A;
+    typedef typename A::Coord Coord;
+    std::vector<A> b(n);
+    for (size_t i = 0; i < n; i++) {
+        std::memcpy(&b[i].x, bases.data() + i * 2 * sizeof(Coord), sizeof(Coord));
+        std::memcpy(&b[i].y, bases.data() + i * 2 * sizeof(Coord) + sizeof(Coord), sizeof(Coord));
+        b[i].infinity = inf[i] != 0;
+    }
+    std::vector<zkm::BigInteger256> s(n);
+    if (n) std::memcpy(s.data(), scal.data(), n * 32);
+    A r = zkm::VariableBaseMSM::multi_scalar_mul<Curve, GROUP>(b, s);
+    bool ok = (int)r.infinity == want_inf && std::memcmp(&r.x, want.data(), sizeof(Coord)) == 0 &&
+              std::memcmp(&r.y, want.data() + sizeof(Coord), sizeof(Coord)) == 0;
+    // the registered path must agree (plain and with precomputed window multiples)
+    for (int pre = 0; pre < 2 && ok && n; pre++) {
+        zkm::RegisteredBases<Curve, GROUP> reg(b, pre != 0);
+        ok = reg.msm(s) == r;
+    }
+    return ok;
+}
+
+template <class Curve>
+static bool run_wmap(int log_n, const std::vector<uint8_t>& a, const std::vector<uint8_t>& b, const std::vector<uint8_t>& c,
+                     const std::vector<uint8_t>& want) {
+    typedef typename Curve::Fr F;
+    auto dom = zkm::Radix2EvaluationDomain<Curve>::new_(size_t(1) << log_n);
+    size_t n = size_t(1) << log_n;
+    std::vector<F> va(n), vb(n), vc(n);
+    std::memcpy(va.data(), a.data(), n * 32);
+    std::memcpy(vb.data(), b.data(), n * 32);
+    std::memcpy(vc.data(), c.data(), n * 32);
+    std::vector<F> h = zkm::witness_map(*dom, va, vb, vc);
+    return std::memcmp(h.data(), want.data(), n * 32) == 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::fprintf(stderr, "usage: %s vectors.txt\n", argv[0]); return 2; }
+    try {
+        zkm::init(0);
+    } catch (const zkm::Error& e) {
+        std::printf("INIT FAILED (%d): %s\n", e.code, e.what());   // expected on a box without a GPU: no CPU fallback
+        return 3;
+    }
+    // error behaviour mirrors upstream: no domain above the two-adicity
+    if (zkm::Radix2EvaluationDomain<zkm::Bn254>::new_((size_t(1) << 28) + 1)) { std::printf("FAIL: domain above two-adicity\n"); return 1; }
+    std::ifstream f(argv[1]);
+    std::string line;
+    int total = 0, bad = 0;
+    while (std::getline(f, line)) {
+        std::istringstream is(line);
+        std::string kind, curve;
+        is >> kind >> curve;
+        bool ok = false;
+        try {
+            if (kind == "ntt") {
+                int log_n, inv, cos; std::string hin, hout;
+                is >> log_n >> inv >> cos >> hin >> hout;
+                ok = curve == "bls12_381" ? run_ntt<zkm::Bls12_381>(log_n, inv, cos, unhex(hin), unhex(hout))
+                                          : run_ntt<zkm::Bn254>(log_n, inv, cos, unhex(hin), unhex(hout));
+            } else if (kind == "msm") {
+                int group, rinf; size_t n; std::string hb, hi, hs, hr;
+                is >> group >> n >> hb >> hi >> hs >> hr >> rinf;
+                auto B = unhex(hb), I = unhex(hi), S = unhex(hs), R = unhex(hr);
+                if (curve == "bls12_381") ok = group == 1 ? run_msm<zkm::Bls12_381, 1>(n, B, I, S, R, rinf) : run_msm<zkm::Bls12_381, 2>(n, B, I, S, R, rinf);
+                else ok = group == 1 ? run_msm<zkm::Bn254, 1>(n, B, I, S, R, rinf) : run_msm<zkm::Bn254, 2>(n, B, I, S, R, rinf);
+            } else if (kind == "wmap") {
+                int log_n; std::string ha, hb, hc, hh;
+                is >> log_n >> ha >> hb >> hc >> hh;
+                ok = curve == "bls12_381" ? run_wmap<zkm::Bls12_381>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh))
+                                          : run_wmap<zkm::Bn254>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh));
+            } else {
+                continue;
+            }
+        } catch (const zkm::Error& e) {
+            std::printf("ERROR (%d): %s\n", e.code, e.what());
+        }
+        total++;
+        if (!ok) { bad++; std::printf("MISMATCH: %s %s (vector %d)\n", kind.c_str(), curve.c_str(), total); }
+    }
+    std::printf("host_cpp: %d vectors, %d mismatches\n", total, bad);
+    zkm_shutdown();
+    return bad ? 1 : (total ? 0 : 2);
+}
