@@ -9,10 +9,13 @@
  *
  * Data formats are arkworks' own, byte for byte:
  *   field element : little-endian u64 limbs, Montgomery form, R = 2^(64*limbs)  (ark-ff Fp256/Fp384)
- *   scalar        : 4 x u64 little-endian, canonical (Fr::into_repr() -> BigInteger256)
+ *   scalar        : S64 x u64 little-endian, canonical (Fr::into_repr() -> BigInteger256 / BigInteger384)
  *   G1 affine     : x, y                      (2 * L64 words)  + a separate infinity byte per point
  *   G2 affine     : x.c0, x.c1, y.c0, y.c1    (4 * L64 words)  + infinity byte
- *   L64 = 6 for BLS12-381 Fq, 4 for BN254 Fq.  Fr is 4 words for both curves.
+ *   L64 = 6 for BLS12-381 Fq, 4 for BN254 Fq; Fr is S64 = 4 words for both.
+ *   BW6-761: L64 = 12 (761-bit Fq), S64 = 6 (377-bit Fr = BLS12-377's Fq); its G2 is a curve over Fq as well,
+ *   so a G2 affine point is x, y (2 * 12 words) exactly like a G1 point.
+ *   Wherever a comment below says "4 words" for an Fr element or scalar, read S64.
  *
  * Every function returns 0 on success or a negative ZKM_ERR_* code; the message of the last
  * failure on the calling thread is available from zkm_last_error().  Nothing throws, aborts or
@@ -37,6 +40,7 @@ extern "C" {
 
 #define ZKM_CURVE_BLS12_381 0
 #define ZKM_CURVE_BN254 1
+#define ZKM_CURVE_BW6_761 2   /* the second curve zkMember benches (/root/reference/benches/groth16.rs:24-29, marlin.rs:40-73) */
 
 #define ZKM_OK 0
 #define ZKM_ERR_ARG (-1)          /* bad curve / group / size / null pointer */
@@ -93,7 +97,7 @@ int32_t zkm_kzg_commit(uint64_t handle, const uint64_t* coeffs, size_t n, uint64
  *   inverse = 0, coset = 1 : coset_fft     x[j] *= g^j first, g = Fr::multiplicative_generator()
  *   inverse = 1, coset = 0 : ifft          includes the multiplication by size_inv
  *   inverse = 1, coset = 1 : coset_ifft    ifft, then x[j] *= g^-j
- * log_n > TWO_ADICITY (32 for BLS12-381 Fr, 28 for BN254 Fr) fails with ZKM_ERR_DOMAIN. */
+ * log_n > TWO_ADICITY (32 for BLS12-381 Fr, 28 for BN254 Fr, 46 for BW6-761 Fr) fails with ZKM_ERR_DOMAIN. */
 int32_t zkm_ntt(int32_t curve, uint64_t* data, uint32_t log_n, int32_t inverse, int32_t coset);
 
 /* Replaces the FFT section of ark_groth16::R1CStoQAP::witness_map (ark-groth16 0.3.0 src/r1cs_to_qap.rs,
@@ -112,9 +116,9 @@ int32_t zkm_witness_map_device(int32_t curve, uint64_t* d_a, uint64_t* d_b, uint
  * create_proof applies to h before the h-query MSM (ark-groth16 0.3.0 src/prover.rs).  In place allowed. */
 int32_t zkm_fr_into_repr_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream);
 
-/* Radix2EvaluationDomain::new: the five domain constants, Montgomery, 4 words each:
+/* Radix2EvaluationDomain::new: the five domain constants, Montgomery, S64 words each:
  * group_gen, group_gen_inv, size_inv, generator (= GENERATOR), generator_inv. */
-int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5x4);
+int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5xS64);
 
 /* ---- device-resident variants ---------------------------------------------------------------
  * Same operations with DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL = the

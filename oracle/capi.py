@@ -5,9 +5,9 @@ arkworks 0.3.0 MSM / radix-2 FFT algorithms (see that file's header for the upst
 and for the PARITY UNPINNED statement).  Arrays are numpy uint64 in arkworks' own formats:
 
   field element   : (..., L64) little-endian u64 limbs, Montgomery (value * 2^(64 L64) mod p)
-  scalar          : (n, 4) canonical little-endian u64 limbs (Fr::into_repr())
+  scalar          : (n, S64) canonical little-endian u64 limbs (Fr::into_repr()); S64 = 4, or 6 for BW6-761
   G1 affine point : (n, 2, L64)       x, y        + separate uint8 infinity flags
-  G2 affine point : (n, 2, 2, L64)    x.c0, x.c1, y.c0, y.c1
+  G2 affine point : (n, 2, 2, L64)    x.c0, x.c1, y.c0, y.c1   (BW6-761: (n, 2, L64) like G1 -- its G2 is over Fq)
 """
 from __future__ import annotations
 
@@ -17,14 +17,14 @@ import subprocess
 
 import numpy as np
 
-from .py.params import BLS12_381, BN254, CurveParams
+from .py.params import BLS12_381, BN254, BW6_761, CurveParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "cpp", "zkm_oracle.cpp")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libzkm_oracle.so")
 
-CURVES = {0: BLS12_381, 1: BN254}
+CURVES = {0: BLS12_381, 1: BN254, 2: BW6_761}
 
 
 def build(force: bool = False) -> str:
@@ -69,7 +69,13 @@ def _p8(a):
 
 
 def coord_words(curve_id: int, group: int) -> int:
-    return CURVES[curve_id].fq.limbs64 * (1 if group == 1 else 2)
+    c = CURVES[curve_id]
+    return c.fq.limbs64 * c.coord_degree(group)
+
+
+def fr_words(curve_id: int) -> int:
+    """u64 words of an Fr element / canonical scalar: 4, or 6 for BW6-761 (BigInteger384)."""
+    return CURVES[curve_id].fr.limbs64
 
 
 def msm(curve_id: int, group: int, bases: np.ndarray, scalars: np.ndarray, infinity=None, threads: int = 0):
@@ -77,7 +83,7 @@ def msm(curve_id: int, group: int, bases: np.ndarray, scalars: np.ndarray, infin
     Returns (xy uint64 array of 2*W words, is_infinity)."""
     W = coord_words(curve_id, group)
     bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 2 * W)
-    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, fr_words(curve_id))
     n = min(len(bases), len(scalars))
     out = np.zeros(2 * W, dtype=np.uint64)
     oinf = np.zeros(1, dtype=np.uint8)
@@ -93,7 +99,7 @@ def msm(curve_id: int, group: int, bases: np.ndarray, scalars: np.ndarray, infin
 
 def ntt(curve_id: int, data: np.ndarray, inverse: bool = False, coset: bool = False, threads: int = 0) -> np.ndarray:
     """Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place on a copy of `data` (n, 4)."""
-    x = np.array(data, dtype=np.uint64, order="C").reshape(-1, 4)
+    x = np.array(data, dtype=np.uint64, order="C").reshape(-1, fr_words(curve_id))
     n = len(x)
     log_n = n.bit_length() - 1
     assert 1 << log_n == n
@@ -105,9 +111,10 @@ def ntt(curve_id: int, data: np.ndarray, inverse: bool = False, coset: bool = Fa
 
 def witness_map(curve_id: int, a: np.ndarray, b: np.ndarray, c: np.ndarray, threads: int = 0) -> np.ndarray:
     """ark-groth16 0.3.0 R1CStoQAP::witness_map after the matrix-vector products: returns h (n, 4)."""
-    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
-    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
-    c = np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4)
+    S = fr_words(curve_id)
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, S)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, S)
+    c = np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, S)
     n = len(a)
     log_n = n.bit_length() - 1
     assert 1 << log_n == n and len(b) == n and len(c) == n
@@ -119,7 +126,7 @@ def witness_map(curve_id: int, a: np.ndarray, b: np.ndarray, c: np.ndarray, thre
 
 
 def domain(curve_id: int, log_n: int) -> dict:
-    out = np.zeros((5, 4), dtype=np.uint64)
+    out = np.zeros((5, fr_words(curve_id)), dtype=np.uint64)
     rc = lib().orc_domain(curve_id, log_n, _p64(out))
     if rc:
         raise ValueError("log_n exceeds two-adicity")
@@ -135,6 +142,8 @@ def generator_mont(curve_id: int, group: int) -> np.ndarray:
         return [(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(L)]
     if group == 1:
         return np.array(fe(c.g1[0]) + fe(c.g1[1]), dtype=np.uint64)
+    if c.g2_over_fq:
+        return np.array(fe(c.g2[0]) + fe(c.g2[1]), dtype=np.uint64)
     (x0, x1), (y0, y1) = c.g2
     return np.array(fe(x0) + fe(x1) + fe(y0) + fe(y1), dtype=np.uint64)
 
@@ -184,17 +193,18 @@ def random_scalars(curve_id: int, n: int, seed: int, kind: str = "uniform") -> n
     width, rejected while >= r (the shape of ark-ff's Fr::rand); 'witness': 45 % zero, 45 % one,
     10 % uniform; 'small': < 2^16."""
     fr = CURVES[curve_id].fr
+    S = fr.limbs64
     rng = np.random.Generator(np.random.PCG64(seed))
-    r_limbs = np.array([(fr.modulus >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
-    top_mask = np.uint64((1 << (fr.bits - 192)) - 1)
+    r_limbs = np.array([(fr.modulus >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(S)], dtype=np.uint64)
+    top_mask = np.uint64((1 << (fr.bits - 64 * (S - 1))) - 1)
 
     def uniform(m):
-        out = rng.integers(0, 1 << 64, size=(m, 4), dtype=np.uint64)
-        out[:, 3] &= top_mask
+        out = rng.integers(0, 1 << 64, size=(m, S), dtype=np.uint64)
+        out[:, S - 1] &= top_mask
         while True:
             ge = np.zeros(m, dtype=bool)
             decided = np.zeros(m, dtype=bool)
-            for j in (3, 2, 1, 0):
+            for j in range(S - 1, -1, -1):
                 gt = (out[:, j] > r_limbs[j]) & ~decided
                 lt = (out[:, j] < r_limbs[j]) & ~decided
                 ge |= gt
@@ -203,14 +213,14 @@ def random_scalars(curve_id: int, n: int, seed: int, kind: str = "uniform") -> n
             k = int(ge.sum())
             if k == 0:
                 return out
-            fresh = rng.integers(0, 1 << 64, size=(k, 4), dtype=np.uint64)
-            fresh[:, 3] &= top_mask
+            fresh = rng.integers(0, 1 << 64, size=(k, S), dtype=np.uint64)
+            fresh[:, S - 1] &= top_mask
             out[ge] = fresh
 
     if kind == "uniform":
         return uniform(n)
     if kind == "small":
-        out = np.zeros((n, 4), dtype=np.uint64)
+        out = np.zeros((n, S), dtype=np.uint64)
         out[:, 0] = rng.integers(0, 1 << 16, size=n, dtype=np.uint64)
         return out
     if kind == "witness":
@@ -218,7 +228,7 @@ def random_scalars(curve_id: int, n: int, seed: int, kind: str = "uniform") -> n
         u = rng.random(n)
         out[u < 0.45] = 0
         ones = (u >= 0.45) & (u < 0.9)
-        out[ones] = np.array([1, 0, 0, 0], dtype=np.uint64)
+        out[ones] = np.array([1] + [0] * (S - 1), dtype=np.uint64)
         return out
     raise ValueError(kind)
 

@@ -107,6 +107,10 @@ static const u64 BN_FQ_P[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb
 static const u64 BN_FR_P[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL,
                                0x30644e72e131a029ULL};
 
+// BW6-761 (ark-bw6-761 0.3.0): Fq is the 761-bit prime of the BW6 family, Fr the 377-bit base field of BLS12-377
+static const u64 BW_FQ_P[12] = {0xf49d00000000008bULL, 0xe6913e6870000082ULL, 0x160cf8aeeaf0a437ULL, 0x98a116c25667a8f8ULL, 0x71dcd3dc73ebff2eULL, 0x8689c8ed12f9fd90ULL, 0x03cebaff25b42304ULL, 0x707ba638e584e919ULL, 0x528275ef8087be41ULL, 0xb926186a81d14688ULL, 0xd187c94004faff3eULL, 0x0122e824fb83ce0aULL};
+static const u64 BW_FR_P[6] = {0x8508c00000000001ULL, 0x170b5d4430000000ULL, 0x1ef3622fba094800ULL, 0x1a22d9f300f5138fULL, 0xc63b05c06ca1493bULL, 0x01ae3a4617c510eaULL};
+
 struct BlsFqTag { static constexpr int N = 6; static const FieldConsts<6> C; };
 struct BlsFrTag { static constexpr int N = 4; static const FieldConsts<4> C; };
 struct BnFqTag  { static constexpr int N = 4; static const FieldConsts<4> C; };
@@ -115,6 +119,10 @@ const FieldConsts<6> BlsFqTag::C = make_consts<6>(BLS_FQ_P);
 const FieldConsts<4> BlsFrTag::C = make_consts<4>(BLS_FR_P);
 const FieldConsts<4> BnFqTag::C = make_consts<4>(BN_FQ_P);
 const FieldConsts<4> BnFrTag::C = make_consts<4>(BN_FR_P);
+struct BwFqTag { static constexpr int N = 12; static const FieldConsts<12> C; };
+struct BwFrTag { static constexpr int N = 6; static const FieldConsts<6> C; };
+const FieldConsts<12> BwFqTag::C = make_consts<12>(BW_FQ_P);
+const FieldConsts<6> BwFrTag::C = make_consts<6>(BW_FR_P);
 
 // ----------------------------------------------------------------------------- Fp (Montgomery)
 template <class T>
@@ -324,18 +332,27 @@ static inline int ceil_log2(size_t a) {  // ark_std::log2
 }
 static inline size_t ln_without_floats(size_t a) { return (size_t)ceil_log2(a) * 69 / 100; }
 
-static inline bool scalar_is_zero(const u64* s) { return (s[0] | s[1] | s[2] | s[3]) == 0; }
-static inline bool scalar_is_one(const u64* s) { return s[0] == 1 && (s[1] | s[2] | s[3]) == 0; }
+// sw = u64 words per scalar: 4 (BigInteger256) or 6 (BigInteger384, BW6-761)
+static inline bool scalar_is_zero(const u64* s, int sw) {
+    u64 o = 0;
+    for (int i = 0; i < sw; i++) o |= s[i];
+    return o == 0;
+}
+static inline bool scalar_is_one(const u64* s, int sw) {
+    u64 o = 0;
+    for (int i = 1; i < sw; i++) o |= s[i];
+    return s[0] == 1 && o == 0;
+}
 // (s >> shift) mod 2^c, c <= 31
-static inline u64 scalar_window(const u64* s, int shift, int c) {
+static inline u64 scalar_window(const u64* s, int sw, int shift, int c) {
     int limb = shift / 64, off = shift % 64;
     u64 v = s[limb] >> off;
-    if (off && limb + 1 < 4) v |= s[limb + 1] << (64 - off);
+    if (off && limb + 1 < sw) v |= s[limb + 1] << (64 - off);
     return v & ((1ULL << c) - 1);
 }
 
 template <class F>
-static Aff<F> msm_arkworks(const Aff<F>* bases, const u64* scalars, size_t size, int num_bits, int threads) {
+static Aff<F> msm_arkworks(const Aff<F>* bases, const u64* scalars, size_t size, int num_bits, int threads, int sw = 4) {
     int c = size < 32 ? 3 : (int)ln_without_floats(size) + 2;
     std::vector<int> window_starts;
     for (int w = 0; w < num_bits; w += c) window_starts.push_back(w);
@@ -347,12 +364,12 @@ static Aff<F> msm_arkworks(const Aff<F>* bases, const u64* scalars, size_t size,
         Jac<F> res = Jac<F>::zero();
         std::vector<Jac<F>> buckets(((size_t)1 << c) - 1, Jac<F>::zero());
         for (size_t i = 0; i < size; i++) {
-            const u64* s = scalars + 4 * i;
-            if (scalar_is_zero(s)) continue;
-            if (scalar_is_one(s)) {
+            const u64* s = scalars + (size_t)sw * i;
+            if (scalar_is_zero(s, sw)) continue;
+            if (scalar_is_one(s, sw)) {
                 if (w_start == 0) res.add_assign_mixed(bases[i]);
             } else {
-                u64 d = scalar_window(s, w_start, c);
+                u64 d = scalar_window(s, sw, w_start, c);
                 if (d != 0) buckets[d - 1].add_assign_mixed(bases[i]);
             }
         }
@@ -381,7 +398,7 @@ struct Domain {
 };
 
 template <class T>
-static bool make_domain(Domain<Fp<T>>& d, int log_n, u64 generator, int two_adicity) {
+static bool make_domain(Domain<Fp<T>>& d, int log_n, long long generator, int two_adicity) {   // generator < 0: p - |g|
     typedef Fp<T> F;
     if (log_n > two_adicity) return false;
     d.log_n = log_n;
@@ -394,7 +411,7 @@ static bool make_domain(Domain<Fp<T>>& d, int log_n, u64 generator, int two_adic
     for (int k = 0; k < two_adicity; k++) {  // e >>= 1
         for (int i = 0; i < T::N; i++) e[i] = (e[i] >> 1) | (i + 1 < T::N ? e[i + 1] << 63 : 0);
     }
-    F g = F::from_u64(generator);
+    F g = generator >= 0 ? F::from_u64((u64)generator) : F::zero() - F::from_u64((u64)(-generator));
     F root = g.pow_limbs(e, T::N);
     for (int k = log_n; k < two_adicity; k++) root = root.sqr();
     d.group_gen = root;
@@ -508,7 +525,7 @@ template <class T> static void store_any(const Fp2<T>& f, u64* dst) { store_any(
 
 template <class F>
 static int run_msm(const u64* bases_xy, const uint8_t* inf, const u64* scalars, size_t n, int num_bits, u64* out_xy,
-                   uint8_t* out_inf, int threads) {
+                   uint8_t* out_inf, int threads, int sw = 4) {
     constexpr int W = F::WORDS;
     std::vector<Aff<F>> b(n);
 #pragma omp parallel for schedule(static)
@@ -517,7 +534,7 @@ static int run_msm(const u64* bases_xy, const uint8_t* inf, const u64* scalars, 
         load_any(b[i].y, bases_xy + 2 * W * i + W);
         b[i].inf = inf ? inf[i] != 0 : false;
     }
-    Aff<F> r = msm_arkworks<F>(b.data(), scalars, n, num_bits, threads);
+    Aff<F> r = msm_arkworks<F>(b.data(), scalars, n, num_bits, threads, sw);
     // the identity is encoded like ark-ec's GroupAffine::zero(): x = 0, y = 1, infinity = true
     store_any(r.x, out_xy);
     store_any(r.y, out_xy + W);
@@ -584,7 +601,7 @@ static int run_progression(const u64* gen_xy, u64 a0, u64 d, size_t n, u64* out_
 }
 
 template <class T>
-static int run_ntt(u64* data, int log_n, int inverse, int coset, u64 generator, int two_adicity, int threads) {
+static int run_ntt(u64* data, int log_n, int inverse, int coset, long long generator, int two_adicity, int threads) {
     Domain<Fp<T>> d;
     if (!make_domain<T>(d, log_n, generator, two_adicity)) return -2;
     if (threads > 0) omp_set_num_threads(threads);
@@ -593,7 +610,7 @@ static int run_ntt(u64* data, int log_n, int inverse, int coset, u64 generator, 
 }
 
 template <class T>
-static int run_domain(int log_n, u64 generator, int two_adicity, u64* out /* 5 x N */) {
+static int run_domain(int log_n, long long generator, int two_adicity, u64* out /* 5 x N */) {
     Domain<Fp<T>> d;
     if (!make_domain<T>(d, log_n, generator, two_adicity)) return -2;
     store_any(d.group_gen, out);
@@ -605,25 +622,29 @@ static int run_domain(int log_n, u64 generator, int two_adicity, u64* out /* 5 x
 }
 
 extern "C" {
-// curve: 0 = BLS12-381, 1 = BN254 (same ids as include/zkm_b200.h).  group: 1 | 2.
-// Formats are arkworks': coordinates Montgomery LE u64 limbs, scalars canonical LE 4 x u64.
+// curve: 0 = BLS12-381, 1 = BN254, 2 = BW6-761 (same ids as include/zkm_b200.h).  group: 1 | 2.
+// Formats are arkworks': coordinates Montgomery LE u64 limbs, scalars canonical LE 4 x u64 (6 x u64 for BW6-761).
 int orc_msm(int curve, int group, const u64* bases_xy, const uint8_t* inf, const u64* scalars, size_t n, u64* out_xy,
             uint8_t* out_inf, int threads) {
     if (curve == 0 && group == 1) return run_msm<Fp<BlsFqTag>>(bases_xy, inf, scalars, n, 255, out_xy, out_inf, threads);
     if (curve == 0 && group == 2) return run_msm<Fp2<BlsFqTag>>(bases_xy, inf, scalars, n, 255, out_xy, out_inf, threads);
     if (curve == 1 && group == 1) return run_msm<Fp<BnFqTag>>(bases_xy, inf, scalars, n, 254, out_xy, out_inf, threads);
     if (curve == 1 && group == 2) return run_msm<Fp2<BnFqTag>>(bases_xy, inf, scalars, n, 254, out_xy, out_inf, threads);
+    // BW6-761: G1 and G2 are both curves over Fq (the group law has a = 0 and never reads b); scalars are 6 x u64
+    if (curve == 2) return run_msm<Fp<BwFqTag>>(bases_xy, inf, scalars, n, 377, out_xy, out_inf, threads, 6);
     return -1;
 }
 int orc_ntt(int curve, u64* data, int log_n, int inverse, int coset, int threads) {
     if (curve == 0) return run_ntt<BlsFrTag>(data, log_n, inverse, coset, 7, 32, threads);
     if (curve == 1) return run_ntt<BnFrTag>(data, log_n, inverse, coset, 5, 28, threads);
+    if (curve == 2) return run_ntt<BwFrTag>(data, log_n, inverse, coset, -5, 46, threads);   // ark-bls12-377 Fq: GENERATOR = -5
     return -1;
 }
 // out: group_gen, group_gen_inv, size_inv, generator, generator_inv  (Montgomery, 4 limbs each)
 int orc_domain(int curve, int log_n, u64* out) {
     if (curve == 0) return run_domain<BlsFrTag>(log_n, 7, 32, out);
     if (curve == 1) return run_domain<BnFrTag>(log_n, 5, 28, out);
+    if (curve == 2) return run_domain<BwFrTag>(log_n, -5, 46, out);
     return -1;
 }
 int orc_progression(int curve, int group, const u64* gen_xy, u64 a0, u64 d, size_t n, u64* out_xy) {
@@ -631,9 +652,10 @@ int orc_progression(int curve, int group, const u64* gen_xy, u64 a0, u64 d, size
     if (curve == 0 && group == 2) return run_progression<Fp2<BlsFqTag>>(gen_xy, a0, d, n, out_xy);
     if (curve == 1 && group == 1) return run_progression<Fp<BnFqTag>>(gen_xy, a0, d, n, out_xy);
     if (curve == 1 && group == 2) return run_progression<Fp2<BnFqTag>>(gen_xy, a0, d, n, out_xy);
+    if (curve == 2) return run_progression<Fp<BwFqTag>>(gen_xy, a0, d, n, out_xy);
     return -1;
 }
-// field: 0 bls fq, 1 bls fr, 2 bn fq, 3 bn fr.  op: 0 mul, 1 add, 2 sub, 3 inverse(a), 4 into_repr(a)
+// field: 0 bls fq, 1 bls fr, 2 bn fq, 3 bn fr, 4 bw6 fq, 5 bw6 fr.  op: 0 mul, 1 add, 2 sub, 3 inverse(a), 4 into_repr(a)
 int orc_field_op(int field, int op, const u64* a, const u64* b, u64* out) {
 #define ORC_FOP(T)                                                        \
     {                                                                     \
@@ -656,6 +678,8 @@ int orc_field_op(int field, int op, const u64* a, const u64* b, u64* out) {
         case 1: ORC_FOP(BlsFrTag)
         case 2: ORC_FOP(BnFqTag)
         case 3: ORC_FOP(BnFrTag)
+        case 4: ORC_FOP(BwFqTag)
+        case 5: ORC_FOP(BwFrTag)
     }
     return -1;
 }
@@ -690,6 +714,7 @@ int orc_witness_map(int curve, const u64* a, const u64* b, const u64* c, int log
     }
     if (curve == 0) ORC_WMAP(BlsFrTag, 7, 32)
     if (curve == 1) ORC_WMAP(BnFrTag, 5, 28)
+    if (curve == 2) ORC_WMAP(BwFrTag, -5, 46)
     return -1;
 }
 int orc_num_threads(void) { return omp_get_max_threads(); }

@@ -103,6 +103,10 @@ class Group:
             self.F = FqOps(curve.fq.modulus)
             self.b = curve.b_g1
             self.gen = curve.g1
+        elif curve.g2_over_fq:       # BW6-761: G2 is a curve over Fq as well
+            self.F = FqOps(curve.fq.modulus)
+            self.b = curve.b_g2
+            self.gen = curve.g2
         else:
             self.F = Fq2Ops(curve.fq.modulus)
             self.b = curve.b_g2
@@ -197,14 +201,14 @@ def scalar_to_bytes(fp: FieldParams, s: int) -> bytes:
 
 
 def coord_to_bytes(curve: CurveParams, g: int, c) -> bytes:
-    if g == 1:
+    if curve.coord_degree(g) == 1:
         return fe_to_bytes(curve.fq, c)
     return fe_to_bytes(curve.fq, c[0]) + fe_to_bytes(curve.fq, c[1])
 
 
 def coord_from_bytes(curve: CurveParams, g: int, b: bytes):
     w = 8 * curve.fq.limbs64
-    if g == 1:
+    if curve.coord_degree(g) == 1:
         return fe_from_bytes(curve.fq, b[:w])
     return (fe_from_bytes(curve.fq, b[:w]), fe_from_bytes(curve.fq, b[w:2 * w]))
 
@@ -213,7 +217,7 @@ def point_to_bytes(curve: CurveParams, g: int, P) -> Tuple[bytes, int]:
     """(xy bytes, infinity flag).  Infinity is encoded like ark-ec's
     GroupAffine::zero(): x = 0, y = 1 (Montgomery one), flag = 1."""
     if P is None:
-        if g == 1:
+        if curve.coord_degree(g) == 1:
             return coord_to_bytes(curve, g, 0) + coord_to_bytes(curve, g, 1), 1
         return coord_to_bytes(curve, g, (0, 0)) + coord_to_bytes(curve, g, (1, 0)), 1
     return coord_to_bytes(curve, g, P[0]) + coord_to_bytes(curve, g, P[1]), 0
@@ -222,7 +226,7 @@ def point_to_bytes(curve: CurveParams, g: int, P) -> Tuple[bytes, int]:
 def point_from_bytes(curve: CurveParams, g: int, b: bytes, inf: int):
     if inf:
         return None
-    w = 8 * curve.fq.limbs64 * g
+    w = 8 * curve.fq.limbs64 * curve.coord_degree(g)
     return (coord_from_bytes(curve, g, b[:w]), coord_from_bytes(curve, g, b[w:2 * w]))
 
 

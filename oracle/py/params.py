@@ -61,8 +61,13 @@ class CurveParams:
     fr: FieldParams
     b_g1: int                    # y^2 = x^3 + b
     g1: tuple                    # generator (x, y)
-    b_g2: tuple                  # (c0, c1) in Fq2 = Fq[u]/(u^2+1)
-    g2: tuple                    # ((x.c0, x.c1), (y.c0, y.c1))
+    b_g2: object                 # (c0, c1) in Fq2 = Fq[u]/(u^2+1); an int when G2 lives over Fq (BW6-761)
+    g2: tuple                    # ((x.c0, x.c1), (y.c0, y.c1)); (x, y) when G2 lives over Fq
+    g2_over_fq: bool = False     # BW6-761: G2 is a second curve over the SAME prime field (M-twist, degree 1)
+
+    def coord_degree(self, g: int) -> int:
+        """Fq elements per coordinate of group g (1 | 2)."""
+        return 2 if (g == 2 and not self.g2_over_fq) else 1
 
 
 # ----------------------------------------------------------------------------- BLS12-381
@@ -138,5 +143,50 @@ BN254 = CurveParams(
     ),
 )
 
-CURVES = {c.name: c for c in (BLS12_381, BN254)}
-CURVES_BY_ID = {c.curve_id: c for c in (BLS12_381, BN254)}
+# ----------------------------------------------------------------------------- BW6-761
+# The other pairing curve zkMember instantiates (/root/reference/benches/groth16.rs:24-29,
+# /root/reference/benches/marlin.rs:40-73; ark-bw6-761 0.3.0).  Fr is the base field of BLS12-377
+# (ark-bw6-761 re-exports ark_bls12_377::Fq as Fr), Fq is the 761-bit prime of the BW6 family
+# q = (t^2 + 3 y^2) / 4 with t = x^5 - 3x^4 + 3x^3 - x + 3 + 13 r, y = (x^5 - 3x^4 + 3x^3 - x + 3)/3 + 9 r,
+# x = 0x8508c00000000001 (checked by tests/test_oracle_constants.py).  G1: y^2 = x^3 - 1, G2: y^2 = x^3 + 4,
+# BOTH over Fq.  FFT constants of Fr as published in ark-bls12-377 0.3.0 src/fields/fq.rs:
+# GENERATOR = -5, TWO_ADICITY = 46, TWO_ADIC_ROOT_OF_UNITY = (-5)^((r-1)/2^46); their Montgomery limbs
+# (0xfc0b8000000002fa, ... / 0x1c104955744e6e0f, ...) are re-derived in the tests.
+# The group generators below are NOT ark-bw6-761's G1/G2_GENERATOR constants (not needed by the hot path:
+# an MSM never touches the generator or the coefficient b); they are the cofactor-cleared points over the
+# smallest x >= 2 with a curve point (smaller y), used only to synthesise test / bench bases.
+BW6_761_FQ = FieldParams(
+    name="bw6_761_fq",
+    modulus=0x122e824fb83ce0ad187c94004faff3eb926186a81d14688528275ef8087be41707ba638e584e91903cebaff25b423048689c8ed12f9fd9071dcd3dc73ebff2e98a116c25667a8f8160cf8aeeaf0a437e6913e6870000082f49d00000000008b,
+    limbs64=12,
+)
+BW6_761_FR = FieldParams(
+    name="bw6_761_fr",
+    modulus=0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001,
+    limbs64=6,
+    generator=0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001 - 5,
+    two_adicity=46,
+    two_adic_root=pow(0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001 - 5,
+                      (0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001 - 1) >> 46,
+                      0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001),
+)
+BW6_761 = CurveParams(
+    name="bw6_761",
+    curve_id=2,
+    fq=BW6_761_FQ,
+    fr=BW6_761_FR,
+    b_g1=BW6_761_FQ.modulus - 1,
+    g1=(
+        0xd82cbf66753123ed25942ffadbec116b901330673728468b1653febae12aa13a5d68dc240a36cfbe185365abc6cb0cc5042c14be9179f0c6c05fc952c93a806d5316c2b601db66bd557011eb2c7dd0c1891418e3ce0e512da946c2ca98c56f,
+        0xa62fd67fdd91e327a96c02bc80385547a171b11241a2653b54d7359cd7569806b159fd05975390f644cd4d4d121918f1f84be0e364c557f196bd4095e732d987ca22009ba7577b80aaa35b641488679ed9ef0d43b32e776ad507137f20a2dd,
+    ),
+    b_g2=4,
+    g2=(
+        0x4cd0ed4bbb4bad28e9646093e4c6ab32a3a80f35265437deef8f50aa1221f459b249d724b2c155e2bf40a492ead210323e3f1c3e6991b9bcabe9da05882daf12d84f49c477fd322fc532b59d18f40b4cc45de6fbd67847acac591e8c5a93fa,
+        0x5bbdc19380f7c707f6fe8680ef10cd46fa210a92bc4f56f1b92ab610ecb3fd508160dc51bab3ee5072aa3dedbe0766414556817439a0fbc33df16a239fc281edec5df53182dcf168c9171615a79353ac90858b4a2f2d20aeae7ededaead5b0,
+    ),
+    g2_over_fq=True,
+)
+
+CURVES = {c.name: c for c in (BLS12_381, BN254, BW6_761)}
+CURVES_BY_ID = {c.curve_id: c for c in (BLS12_381, BN254, BW6_761)}

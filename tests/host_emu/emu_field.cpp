@@ -94,13 +94,15 @@ static void curve_ops(int op, const uint32_t* p, const uint32_t* q, uint32_t* ou
 }
 
 extern "C" {
-// field: 0 bls fq, 1 bls fr, 2 bn fq, 3 bn fr
+// field: 0 bls fq, 1 bls fr, 2 bn fq, 3 bn fr, 4 bw6 fq (24 limbs), 5 bw6 fr (12 limbs)
 int emu_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, int count) {
     switch (field) {
         case 0: fp_ops<Bls12_381_Fq>(op, a, b, out, count); return 0;
         case 1: fp_ops<Bls12_381_Fr>(op, a, b, out, count); return 0;
         case 2: fp_ops<Bn254_Fq>(op, a, b, out, count); return 0;
         case 3: fp_ops<Bn254_Fr>(op, a, b, out, count); return 0;
+        case 4: fp_ops<Bw6_761_Fq>(op, a, b, out, count); return 0;
+        case 5: fp_ops<Bw6_761_Fr>(op, a, b, out, count); return 0;
     }
     return -1;
 }
@@ -115,6 +117,7 @@ int emu_curve_op(int curve, int group, int op, const uint32_t* p, const uint32_t
     else if (curve == 0 && group == 2) curve_ops<Bls12_381_Fq2>(op, p, q, out, out_inf, count);
     else if (curve == 1 && group == 1) curve_ops<Bn254_Fq>(op, p, q, out, out_inf, count);
     else if (curve == 1 && group == 2) curve_ops<Bn254_Fq2>(op, p, q, out, out_inf, count);
+    else if (curve == 2) curve_ops<Bw6_761_Fq>(op, p, q, out, out_inf, count);   // G1 and G2 both over Fq
     else return -1;
     return 0;
 }

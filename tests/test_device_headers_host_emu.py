@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle.py import exact
-from oracle.py.params import BLS12_381, BN254
+from oracle.py.params import BLS12_381, BN254, BW6_761
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emu", "emu_field.cpp")
@@ -27,7 +27,7 @@ def emu():
     return ctypes.CDLL(OUT)
 
 
-FIELDS = {0: BLS12_381.fq, 1: BLS12_381.fr, 2: BN254.fq, 3: BN254.fr}
+FIELDS = {0: BLS12_381.fq, 1: BLS12_381.fr, 2: BN254.fq, 3: BN254.fr, 4: BW6_761.fq, 5: BW6_761.fr}
 
 
 def _limbs32(v, n):
@@ -38,12 +38,12 @@ def _p(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3, 4, 5])
 def test_fp_ops(emu, fid):
     fp = FIELDS[fid]
     p, n = fp.modulus, fp.limbs32
     rng = np.random.default_rng(fid)
-    vals = [0, 1, 2, p - 1, p - 2, (p - 1) // 2] + [int.from_bytes(rng.bytes(48), "little") % p for _ in range(60)]
+    vals = [0, 1, 2, p - 1, p - 2, (p - 1) // 2] + [int.from_bytes(rng.bytes(104), "little") % p for _ in range(60)]
     A = np.array([_limbs32(fp.to_mont(v), n) for v in vals], dtype=np.uint32)
     B = np.array([_limbs32(fp.to_mont(v), n) for v in reversed(vals)], dtype=np.uint32)
     out = np.zeros_like(A)
@@ -61,7 +61,7 @@ def test_fp_ops(emu, fid):
     for i, a in enumerate(nz):
         assert sum(int(out2[i, j]) << (32 * j) for j in range(n)) == fp.to_mont(pow(a, -1, p))
     # binary-EGCD inverse == Fermat inverse, incl. 1, p-1, small values and inv(0) = 0
-    edge = [1, 2, 3, p - 1, p - 2, (p + 1) // 2] + [int.from_bytes(rng.bytes(48), "little") % p for _ in range(30)]
+    edge = [1, 2, 3, p - 1, p - 2, (p + 1) // 2] + [int.from_bytes(rng.bytes(104), "little") % p for _ in range(30)]
     A3 = np.array([_limbs32(fp.to_mont(v), n) for v in edge], dtype=np.uint32)
     o5, o7 = np.zeros_like(A3), np.zeros_like(A3)
     assert emu.emu_fp_op(fid, 5, _p(A3), _p(A3), _p(o5), len(edge)) == 0
@@ -74,22 +74,23 @@ def test_fp_ops(emu, fid):
     assert emu.emu_fp_op(fid, 5, _p(Z), _p(Z), _p(oz), 1) == 0 and not oz.any()
 
 
-@pytest.mark.parametrize("curve", [BLS12_381, BN254], ids=lambda c: c.name)
+@pytest.mark.parametrize("curve", [BLS12_381, BN254, BW6_761], ids=lambda c: c.name)
 @pytest.mark.parametrize("g", [1, 2])
 def test_xyzz_group_law_with_exceptional_cases(emu, curve, g):
     """madd / add / dbl / to_affine incl. identity operands, P + P and P + (-P)."""
     G = exact.Group(curve, g)
     fq = curve.fq
-    n = fq.limbs32 * g
+    deg = curve.coord_degree(g)
+    n = fq.limbs32 * deg
     pts = G.progression(3, 5, 6)
 
     def coord(c):
-        if g == 1:
+        if deg == 1:
             return _limbs32(fq.to_mont(c), fq.limbs32)
         return _limbs32(fq.to_mont(c[0]), fq.limbs32) + _limbs32(fq.to_mont(c[1]), fq.limbs32)
 
-    one = 1 if g == 1 else (1, 0)
-    zero = 0 if g == 1 else (0, 0)
+    one = 1 if deg == 1 else (1, 0)
+    zero = 0 if deg == 1 else (0, 0)
 
     def xyzz(P):
         if P is None:

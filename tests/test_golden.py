@@ -11,7 +11,12 @@ from oracle import capi
 HERE = os.path.dirname(os.path.abspath(__file__))
 NTT = json.load(open(os.path.join(HERE, "golden", "ntt_vectors.json")))["vectors"]
 MSM = json.load(open(os.path.join(HERE, "golden", "msm_vectors.json")))["vectors"]
-CID = {"bls12_381": 0, "bn254": 1}
+CID = {"bls12_381": 0, "bn254": 1, "bw6_761": 2}
+SW = {"bls12_381": 4, "bn254": 4, "bw6_761": 6}       # u64 words per Fr element / scalar
+
+
+def _coord_words(curve, group):
+    return capi.coord_words(CID[curve], group)
 
 
 def _u64(hexstr, cols):
@@ -34,15 +39,15 @@ def test_golden_files_are_reproducible():
 @pytest.mark.parametrize("i", range(len(NTT)))
 def test_oracle_ntt_golden(i):
     v = NTT[i]
-    got = capi.ntt(CID[v["curve"]], _u64(v["input"], 4), v["inverse"], v["coset"])
+    got = capi.ntt(CID[v["curve"]], _u64(v["input"], SW[v["curve"]]), v["inverse"], v["coset"])
     assert got.tobytes().hex() == v["output"]
 
 
 @pytest.mark.parametrize("i", range(len(MSM)))
 def test_oracle_msm_golden(i):
     v = MSM[i]
-    W = (6 if v["curve"] == "bls12_381" else 4) * v["group"]
-    xy, inf = capi.msm(CID[v["curve"]], v["group"], _u64(v["bases"], 2 * W), _u64(v["scalars"], 4),
+    W = _coord_words(v["curve"], v["group"])
+    xy, inf = capi.msm(CID[v["curve"]], v["group"], _u64(v["bases"], 2 * W), _u64(v["scalars"], SW[v["curve"]]),
                        np.array(v["infinity"], dtype=np.uint8))
     assert int(inf) == v["result_infinity"] and xy.tobytes().hex() == v["result"]
 
@@ -53,7 +58,7 @@ def test_gpu_ntt_golden():
     zkm.init(0)
     for v in NTT:
         dom = zkm.Radix2EvaluationDomain(v["curve"], v["log_n"])
-        x = _u64(v["input"], 4)
+        x = _u64(v["input"], SW[v["curve"]])
         fn = {(False, False): dom.fft, (True, False): dom.ifft, (False, True): dom.coset_fft, (True, True): dom.coset_ifft}
         assert fn[(v["inverse"], v["coset"])](x).tobytes().hex() == v["output"], v["log_n"]
 
@@ -63,7 +68,7 @@ def test_gpu_msm_golden():
     import zkmember_b200 as zkm
     zkm.init(0)
     for v in MSM:
-        W = (6 if v["curve"] == "bls12_381" else 4) * v["group"]
-        got = zkm.VariableBaseMSM.multi_scalar_mul(_u64(v["bases"], 2 * W), _u64(v["scalars"], 4), curve=v["curve"],
+        W = _coord_words(v["curve"], v["group"])
+        got = zkm.VariableBaseMSM.multi_scalar_mul(_u64(v["bases"], 2 * W), _u64(v["scalars"], SW[v["curve"]]), curve=v["curve"],
                                                    group=v["group"], infinity=np.array(v["infinity"], dtype=np.uint8))
         assert int(got.infinity) == v["result_infinity"] and got.xy.tobytes().hex() == v["result"], (v["curve"], v["group"], v["n"])

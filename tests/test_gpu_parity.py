@@ -9,11 +9,11 @@ import pytest
 
 from oracle import capi
 from oracle.py import exact
-from oracle.py.params import BLS12_381, BN254
+from oracle.py.params import BLS12_381, BN254, BW6_761
 
 pytestmark = pytest.mark.gpu
 
-CURVES = [BLS12_381, BN254]
+CURVES = [BLS12_381, BN254, BW6_761]   # BW6-761: 761-bit Fq (G1 and G2), 377-bit Fr, 6-word scalars
 MODES = [(False, False), (True, False), (False, True), (True, True)]
 
 
@@ -60,7 +60,7 @@ def test_ntt_zero_padding_and_definition(zkm, curve):
     x = [3, 1, 4, 1, 5]
     dom = zkm.Radix2EvaluationDomain.new(len(x), curve.name)
     assert dom.size == 8
-    data = capi.ints_to_limbs([fr.to_mont(v) for v in x], 4)
+    data = capi.ints_to_limbs([fr.to_mont(v) for v in x], fr.limbs64)
     got = capi.limbs_to_ints(dom.fft(data))
     want = exact.ntt_def(fr, x + [0, 0, 0])
     assert got == [fr.to_mont(v) for v in want]
@@ -232,7 +232,7 @@ def test_msm_known_discrete_log_large(zkm, curve, log_n, kind):
     import torch
     n = 1 << log_n      # 2^22 x 16 windows crosses the threshold of the batched-affine pairwise levels
     a0, d = 0x1234567, 0x89ABCDE
-    W = 6 if curve.curve_id == 0 else 4
+    W = curve.fq.limbs64
     dev = torch.device("cuda:0")
     d_bases = torch.empty((n, 2 * W), dtype=torch.int64, device=dev)
     L = zkm._lib.lib()
@@ -248,7 +248,7 @@ def test_msm_known_discrete_log_large(zkm, curve, log_n, kind):
     reg.release()
     r = curve.fr.modulus
     s_int = scal.astype(object)
-    s_vals = s_int[:, 0] + (s_int[:, 1] << 64) + (s_int[:, 2] << 128) + (s_int[:, 3] << 192)
+    s_vals = sum(s_int[:, j] << (64 * j) for j in range(curve.fr.limbs64))
     idx = np.arange(n, dtype=object)
     k = int(np.sum(s_vals * (a0 + idx * d)) % r)
     G = exact.Group(curve, 1)
@@ -266,7 +266,7 @@ def test_points_sum_device(zkm, curve, g):
     pts = G.progression(5, 9, 6)
     pts[2] = None
     pts[4] = pts[3]
-    W = curve.fq.limbs64 * g
+    W = curve.fq.limbs64 * curve.coord_degree(g)
     rec = np.zeros((len(pts), 2 * W + 1), dtype=np.uint64)
     for i, P in enumerate(pts):
         b, f = exact.point_to_bytes(curve, g, P)
@@ -393,7 +393,7 @@ def test_kzg_commit_matches_oracle(zkm, curve, precompute):
     n = 1500
     powers = capi.progression(curve.curve_id, 1, 5, 3, n)       # stand-in SRS (any G1 points)
     pw = Powers(curve.name, powers, precompute=precompute)
-    fid = 1 if curve.curve_id == 0 else 3
+    fid = {0: 1, 1: 3, 2: 5}[curve.curve_id]
     try:
         for deg, lead in ((n - 1, 0), (999, 7), (10, 11), (0, 0)):
             coeffs = capi.random_field_elements(curve.curve_id, deg + 1, seed=deg + lead)
@@ -402,7 +402,7 @@ def test_kzg_commit_matches_oracle(zkm, curve, precompute):
             while z < len(coeffs) and not coeffs[z].any():
                 z += 1
             repr_ = np.stack([capi.field_op(fid, 4, coeffs[i]) for i in range(z, len(coeffs))]) if z < len(coeffs) \
-                else np.zeros((0, 4), dtype=np.uint64)
+                else np.zeros((0, fr.limbs64), dtype=np.uint64)
             want_xy, want_inf = capi.msm(curve.curve_id, 1, powers[z:z + len(repr_)], repr_)
             got = KZG10.commit(pw, coeffs)
             _check_point(curve, 1, got, want_xy, want_inf)

@@ -7,22 +7,22 @@ import pytest
 
 from oracle import capi
 from oracle.py import exact
-from oracle.py.params import BLS12_381, BN254
+from oracle.py.params import BLS12_381, BN254, BW6_761
 
-CURVES = [BLS12_381, BN254]
-FIELDS = {0: BLS12_381.fq, 1: BLS12_381.fr, 2: BN254.fq, 3: BN254.fr}
+CURVES = [BLS12_381, BN254, BW6_761]
+FIELDS = {0: BLS12_381.fq, 1: BLS12_381.fr, 2: BN254.fq, 3: BN254.fr, 4: BW6_761.fq, 5: BW6_761.fr}
 
 
 def _fe(fp, v):
     return capi.ints_to_limbs([fp.to_mont(v)], fp.limbs64)[0]
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3, 4, 5])
 def test_field_ops_match_bigint(fid):
     fp = FIELDS[fid]
     rng = np.random.default_rng(100 + fid)
     p = fp.modulus
-    vals = [0, 1, p - 1, 2, (p - 1) // 2] + [int.from_bytes(rng.bytes(48), "little") % p for _ in range(40)]
+    vals = [0, 1, p - 1, 2, (p - 1) // 2] + [int.from_bytes(rng.bytes(104), "little") % p for _ in range(40)]
     for a in vals:
         for b in vals[:8]:
             A, B = _fe(fp, a), _fe(fp, b)
@@ -48,6 +48,39 @@ def test_published_montgomery_constants():
     assert one == 1
 
 
+def test_bw6_761_constants():
+    """BW6-761 (ark-bw6-761 0.3.0 / ark-bls12-377 0.3.0) is not vendored either: the moduli are pinned by the
+    family polynomials, the FFT constants by the published Montgomery limbs of ark-bls12-377's fq.rs."""
+    from sympy import isprime
+    x = 0x8508c00000000001                                   # the BLS12-377 seed
+    r377 = x ** 4 - x ** 2 + 1
+    q377 = (x - 1) ** 2 * r377 // 3 + x
+    assert BW6_761.fr.modulus == q377 and isprime(q377) and q377.bit_length() == 377
+    t0 = x ** 5 - 3 * x ** 4 + 3 * x ** 3 - x + 3            # BW6 family, h_t = 13, h_y = 9
+    t, y = t0 + 13 * q377, t0 // 3 + 9 * q377
+    assert (t * t + 3 * y * y) % 4 == 0 and (t * t + 3 * y * y) // 4 == BW6_761.fq.modulus
+    assert isprime(BW6_761.fq.modulus) and BW6_761.fq.bits == 761
+    fr = BW6_761.fr
+
+    def limbs(v, n):
+        return [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)]
+    # ark-bls12-377 0.3.0 src/fields/fq.rs: TWO_ADICITY = 46, GENERATOR = -5, R, TWO_ADIC_ROOT_OF_UNITY (Montgomery limbs)
+    assert fr.two_adicity == 46 and (fr.modulus - 1) % (1 << 46) == 0 and ((fr.modulus - 1) >> 46) % 2 == 1
+    assert fr.generator == fr.modulus - 5
+    assert limbs(fr.to_mont(1), 6)[:2] == [0x02cdffffffffff68, 0x51409f837fffffb1]
+    assert limbs(fr.to_mont(fr.generator), 6) == [0xfc0b8000000002fa, 0x97d39cf6e000018b, 0x2072420fbfa05044,
+                                                   0xcbbcbd50d97c3802, 0x0baf1ec35813f9eb, 0x009974a2c0945ad2]
+    assert limbs(fr.to_mont(fr.two_adic_root), 6) == [0x1c104955744e6e0f, 0xf1bd15c3898dd1af, 0x76da78169a7f3950,
+                                                       0xee086c1fe367c337, 0xf95564f4cbc1b61f, 0x00f3c1414ef58c54]
+    assert pow(fr.two_adic_root, 1 << 45, fr.modulus) == fr.modulus - 1          # order exactly 2^46
+    # ark-bw6-761 0.3.0 src/fields/fq.rs: R = 0x0202ffffffff85d5, 0x5a5826358fff8ce7, 0x9e996e43827faade, ...
+    assert limbs(BW6_761.fq.to_mont(1), 12)[:3] == [0x0202ffffffff85d5, 0x5a5826358fff8ce7, 0x9e996e43827faade]
+    # G1: y^2 = x^3 - 1, G2: y^2 = x^3 + 4, both over Fq; the synthetic generators have order r
+    for g in (1, 2):
+        G = exact.Group(BW6_761, g)
+        assert G.on_curve(G.gen) and G.mul(G.gen, fr.modulus) is None
+
+
 @pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
 @pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8])
 @pytest.mark.parametrize("inverse,coset", [(0, 0), (1, 0), (0, 1), (1, 1)])
@@ -55,9 +88,9 @@ def test_ntt_matches_definition(curve, log_n, inverse, coset):
     fr = curve.fr
     n = 1 << log_n
     rng = np.random.default_rng(7 * log_n + inverse + 2 * coset)
-    x = [int.from_bytes(rng.bytes(40), "little") % fr.modulus for _ in range(n)]
+    x = [int.from_bytes(rng.bytes(56), "little") % fr.modulus for _ in range(n)]
     want = exact.ntt_def(fr, x, bool(inverse), bool(coset)) if n <= 256 else exact.ntt_fast(fr, x, bool(inverse), bool(coset))
-    data = capi.ints_to_limbs([fr.to_mont(v) for v in x], 4)
+    data = capi.ints_to_limbs([fr.to_mont(v) for v in x], fr.limbs64)
     got = capi.ntt(curve.curve_id, data, bool(inverse), bool(coset))
     assert capi.limbs_to_ints(got) == [fr.to_mont(v) for v in want]
 
@@ -94,7 +127,7 @@ def test_domain_constants(curve):
 
 
 def _points_to_array(curve, g, pts):
-    W = curve.fq.limbs64 * g
+    W = curve.fq.limbs64 * curve.coord_degree(g)
     arr = np.zeros((len(pts), 2 * W), dtype=np.uint64)
     inf = np.zeros(len(pts), dtype=np.uint8)
     for i, P in enumerate(pts):

@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle.py import exact  # noqa: E402
-from oracle.py.params import BLS12_381, BN254  # noqa: E402
+from oracle.py.params import BLS12_381, BN254, BW6_761  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -27,7 +27,7 @@ def hexs(b: bytes) -> str:
 
 def ntt_vectors():
     vecs = []
-    for curve in (BLS12_381, BN254):
+    for curve in (BLS12_381, BN254, BW6_761):
         fr = curve.fr
         rng = random.Random(1000 + curve.curve_id)
         for log_n in (0, 1, 3, 4, 6):
@@ -48,7 +48,7 @@ def ntt_vectors():
 
 def msm_vectors():
     vecs = []
-    for curve in (BLS12_381, BN254):
+    for curve in (BLS12_381, BN254, BW6_761):
         for g in (1, 2):
             G = exact.Group(curve, g)
             rng = random.Random(2000 + 10 * curve.curve_id + g)

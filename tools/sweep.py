@@ -32,7 +32,7 @@ ap.add_argument("--precompute", action="store_true")
 ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle (arkworks algorithm restated) up to 2^20")
 args = ap.parse_args()
 
-cid = {"bls12_381": 0, "bn254": 1}[args.curve]
+cid = {"bls12_381": 0, "bn254": 1, "bw6_761": 2}[args.curve]
 zkm.init(0)
 L = _lib.lib()
 dev = torch.device("cuda:0")
@@ -58,7 +58,7 @@ def timeit(fn, reps):
 
 
 if args.what == "msm":
-    W = (6 if cid == 0 else 4) * args.group
+    W = capi.coord_words(cid, args.group)
     nmax = 1 << args.max
     d_bases = torch.empty((nmax, 2 * W), dtype=torch.int64, device=dev)
     _lib.check(L.zkm_testgen_progression_device(cid, args.group, 0x1234567, 0x89ABCDE, nmax,
@@ -101,7 +101,7 @@ else:
             med, best = timeit(lambda: _lib.check(L.zkm_ntt_device(cid, ctypes.c_void_p(x.data_ptr()),
                                                                    ctypes.c_void_p(y.data_ptr()), lg, inv, cos, sp)), args.reps)
             row[name + "_ms"] = med
-        row["hbm_frac_fft"] = 64.0 * n / (row["fft_ms"] * 1e-3) / 6539.9e9
+        row["hbm_frac_fft"] = 2.0 * 8 * capi.fr_words(cid) * n / (row["fft_ms"] * 1e-3) / 6539.9e9
         if args.cpu and lg <= 22:
             import time
             t0 = time.perf_counter()

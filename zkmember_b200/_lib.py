@@ -14,7 +14,10 @@ LIB_PATH = os.path.join(HERE, "lib", "libzkm_b200.so")
 
 CURVE_BLS12_381 = 0
 CURVE_BN254 = 1
-CURVE_IDS = {"bls12_381": CURVE_BLS12_381, "bn254": CURVE_BN254}
+CURVE_BW6_761 = 2
+CURVE_IDS = {"bls12_381": CURVE_BLS12_381, "bn254": CURVE_BN254, "bw6_761": CURVE_BW6_761}
+# u64 words of an Fr element / canonical scalar (BigInteger256; BigInteger384 for BW6-761)
+FR_WORDS = {CURVE_BLS12_381: 4, CURVE_BN254: 4, CURVE_BW6_761: 6}
 
 ERR_NAMES = {
     -1: "ZKM_ERR_ARG", -2: "ZKM_ERR_CUDA", -3: "ZKM_ERR_NOT_INIT", -4: "ZKM_ERR_DOMAIN",

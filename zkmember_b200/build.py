@@ -28,6 +28,8 @@ UNITS = [
     "zkm_msm_g2_bls.cu",
     "zkm_msm_g1_bn.cu",
     "zkm_msm_g2_bn.cu",
+    "zkm_ntt_bw6.cu",
+    "zkm_msm_bw6.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -52,6 +54,8 @@ UNIT_HEADERS = {
     "zkm_msm_g2_bls.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
     "zkm_msm_g1_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
     "zkm_msm_g2_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
+    "zkm_ntt_bw6.cu": ["zkm_ntt.cuh"],
+    "zkm_msm_bw6.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
 }
 
 

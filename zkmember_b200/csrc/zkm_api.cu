@@ -76,7 +76,7 @@ static int32_t guarded(Fn&& fn) {
 }
 
 static void check_curve_group(int curve, int group) {
-    if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+    if (!curve_known(curve)) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
     if (group != 1 && group != 2) ZKM_FAIL(ZKM_ERR_ARG, "group must be 1 or 2, got %d", group);
 }
 
@@ -91,9 +91,10 @@ static void msm_host(Context* c, int curve, int group, const void* d_bases, cons
     if (n && !scalars) ZKM_FAIL(ZKM_ERR_ARG, "null scalars");
     const int W = coord_words(curve, group);
     c->begin(c->stream);
-    uint64_t* d_scal = (uint64_t*)c->io_scalars.get((n ? n : 1) * 32);
+    const size_t sbytes = (size_t)fr_words(curve) * 8;   // BigInteger256 / BigInteger384
+    uint64_t* d_scal = (uint64_t*)c->io_scalars.get((n ? n : 1) * sbytes);
     uint64_t* d_out = (uint64_t*)c->io_out.get((2 * W + 1) * 8);
-    h2d(d_scal, scalars, n * 32, c->stream);
+    h2d(d_scal, scalars, n * sbytes, c->stream);
     msm_run(c, curve, group, d_bases, d_inf, d_scal, n, d_out, c->stream, pre, pre_offset);
     uint64_t* h = (uint64_t*)c->pin_in.get((2 * W + 1) * 8);
     ZKM_CUDA(cudaMemcpyAsync(h, d_out, (2 * W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -312,17 +313,24 @@ int32_t zkm_kzg_commit(uint64_t handle, const uint64_t* coeffs, size_t n, uint64
         if (!out_xy || !out_inf || (n && !coeffs)) ZKM_FAIL(ZKM_ERR_ARG, "null pointer");
         ZKM_CUDA(cudaSetDevice(c->device));
         // skip_leading_zeros_and_convert_to_bigints: drop the zero coefficients at the low end, keep the offset
+        const BasesReg r0 = lookup(c, handle, 0, 0);
+        const size_t S = (size_t)fr_words(r0.curve);
         size_t z = 0;
-        while (z < n && (coeffs[4 * z] | coeffs[4 * z + 1] | coeffs[4 * z + 2] | coeffs[4 * z + 3]) == 0) z++;
+        auto coeff_is_zero = [&](size_t i) {
+            uint64_t o = 0;
+            for (size_t k = 0; k < S; k++) o |= coeffs[S * i + k];
+            return o == 0;
+        };
+        while (z < n && coeff_is_zero(z)) z++;
         const size_t m = n - z;
         const BasesReg r = lookup(c, handle, z, m);
         if (r.group != 1) ZKM_FAIL(ZKM_ERR_ARG, "KZG powers must be G1 bases");
         const int W = coord_words(r.curve, r.group);
         const size_t rec = 2 * (size_t)W * 8;
         c->begin(c->stream);
-        uint64_t* d_scal = (uint64_t*)c->io_scalars.get((m ? m : 1) * 32);
+        uint64_t* d_scal = (uint64_t*)c->io_scalars.get((m ? m : 1) * S * 8);
         uint64_t* d_out = (uint64_t*)c->io_out.get((2 * W + 1) * 8);
-        h2d(d_scal, coeffs + 4 * z, m * 32, c->stream);
+        h2d(d_scal, coeffs + S * z, m * S * 8, c->stream);
         fr_into_repr_run(c, r.curve, d_scal, d_scal, (uint64_t)m, c->stream);   // coeffs.into_repr()
         msm_run(c, r.curve, r.group, (const char*)r.d_xy + z * rec, r.d_inf ? r.d_inf + z : nullptr, d_scal, m, d_out,
                 c->stream, &r, z);
@@ -424,13 +432,13 @@ int32_t zkm_ntt(int32_t curve, uint64_t* data, uint32_t log_n, int32_t inverse, 
     return guarded([&] {
         LaneGuard lane;
         Context* c = lane.c;
-        if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+        if (!curve_known(curve)) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
         if (!data) ZKM_FAIL(ZKM_ERR_ARG, "null data");
-        const int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
+        const int adicity = fr_two_adicity(curve);
         if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
         if (log_n > 30) ZKM_FAIL(ZKM_ERR_ARG, "log_n %u: domains above 2^30 are not supported by this build", log_n);
         ZKM_CUDA(cudaSetDevice(c->device));
-        const size_t bytes = (size_t)32 << log_n;
+        const size_t bytes = ((size_t)fr_words(curve) * 8) << log_n;
         c->begin(c->stream);
         uint64_t* d_a = (uint64_t*)c->io_scalars.get(bytes);
         uint64_t* d_b = (uint64_t*)c->ntt_b.get(bytes);
@@ -485,12 +493,12 @@ int32_t zkm_witness_map(int32_t curve, const uint64_t* a, const uint64_t* b, con
         LaneGuard lane;
         Context* c = lane.c;
         if (!a || !b || !cc || !h_out) ZKM_FAIL(ZKM_ERR_ARG, "null pointer");
-        const int adicity = curve == ZKM_CURVE_BLS12_381 ? 32 : 28;
-        if (curve != ZKM_CURVE_BLS12_381 && curve != ZKM_CURVE_BN254) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+        if (!curve_known(curve)) ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+        const int adicity = fr_two_adicity(curve);
         if ((int)log_n > adicity) ZKM_FAIL(ZKM_ERR_DOMAIN, "log_n %u exceeds the two-adicity %d of Fr", log_n, adicity);
         if (log_n > 28) ZKM_FAIL(ZKM_ERR_ARG, "log_n %u: witness maps above 2^28 are not supported by this build", log_n);
         ZKM_CUDA(cudaSetDevice(c->device));
-        const size_t bytes = (size_t)32 << log_n;
+        const size_t bytes = ((size_t)fr_words(curve) * 8) << log_n;
         c->begin(c->stream);
         char* d = (char*)c->io_scalars.get(4 * bytes);
         h2d(d, a, bytes, c->stream);

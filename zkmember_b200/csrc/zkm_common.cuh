@@ -176,9 +176,18 @@ struct LaneGuard {
 };
 
 Context* ctx();            // lane 0 (non-compute queries); throws ZKM_ERR_NOT_INIT when zkm_init has not succeeded
+inline bool curve_known(int curve) {
+    return curve == ZKM_CURVE_BLS12_381 || curve == ZKM_CURVE_BN254 || curve == ZKM_CURVE_BW6_761;
+}
+// u64 words per coordinate: Fq for G1, Fq2 for G2 -- except BW6-761, whose G2 is a curve over Fq as well
 inline int coord_words(int curve, int group) {
+    if (curve == ZKM_CURVE_BW6_761) return 12;
     return (curve == ZKM_CURVE_BLS12_381 ? 6 : 4) * (group == 2 ? 2 : 1);
 }
+// u64 words of a scalar-field element / canonical scalar: BigInteger256, or BigInteger384 for BW6-761
+inline int fr_words(int curve) { return curve == ZKM_CURVE_BW6_761 ? 6 : 4; }
+inline int fr_two_adicity(int curve) { return curve == ZKM_CURVE_BLS12_381 ? 32 : (curve == ZKM_CURVE_BN254 ? 28 : 46); }
+inline int fr_bits(int curve) { return curve == ZKM_CURVE_BLS12_381 ? 255 : (curve == ZKM_CURVE_BN254 ? 254 : 377); }
 
 // entry points implemented by the two compute translation units
 void ntt_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n, int inverse, int coset,

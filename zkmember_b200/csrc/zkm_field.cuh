@@ -1,5 +1,5 @@
 // zkm_field.cuh -- Montgomery prime fields on 32-bit limbs and the quadratic
-// extension Fq2 = Fq[u]/(u^2+1) used by G2 of both BLS12-381 and BN254.
+// extension Fq2 = Fq[u]/(u^2+1) used by G2 of both BLS12-381 and BN254 (BW6-761's G2 is over Fq itself).
 //
 // Semantics replaced (un-vendored ark-ff 0.3.0, pinned at
 // /root/reference/Cargo.lock:229-230): Fp256/Fp384 mul_assign / square_in_place /
@@ -17,7 +17,7 @@
 // aligned register pair.  Column j of the two accumulators is merged right before
 // the reduction factor m_j is formed; the carry of a chain lands in a column no
 // chain body has reached yet, so it can never overflow.  Requires a spare top bit
-// in the modulus (381/384, 255/256, 254/256 here).
+// in the modulus (381/384, 255/256, 254/256, 761/768, 377/384 here).
 #pragma once
 #include "zkm_arith.cuh"
 #include "zkm_constants.cuh"
@@ -40,6 +40,8 @@ ZKM_DEFINE_FP_PARAMS(Bls12_381_FqP, BLS12_381_FQ, 12)
 ZKM_DEFINE_FP_PARAMS(Bls12_381_FrP, BLS12_381_FR, 8)
 ZKM_DEFINE_FP_PARAMS(Bn254_FqP, BN254_FQ, 8)
 ZKM_DEFINE_FP_PARAMS(Bn254_FrP, BN254_FR, 8)
+ZKM_DEFINE_FP_PARAMS(Bw6_761_FqP, BW6_761_FQ, 24)
+ZKM_DEFINE_FP_PARAMS(Bw6_761_FrP, BW6_761_FR, 12)   // = the base field of BLS12-377
 
 // ----------------------------------------------------------------------------- Fp
 template <class P>
@@ -389,5 +391,7 @@ typedef Fp<Bn254_FqP> Bn254_Fq;
 typedef Fp<Bn254_FrP> Bn254_Fr;
 typedef Fp2<Bls12_381_FqP> Bls12_381_Fq2;
 typedef Fp2<Bn254_FqP> Bn254_Fq2;
+typedef Fp<Bw6_761_FqP> Bw6_761_Fq;   // G1 AND G2 of BW6-761 live over this 761-bit prime field
+typedef Fp<Bw6_761_FrP> Bw6_761_Fr;
 
 }  // namespace zkm

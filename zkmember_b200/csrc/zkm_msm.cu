@@ -30,24 +30,31 @@ namespace zkm {
 // MODE 0: histogram into counts[K] (all windows).  MODE 1: scatter (index | sign << 31) at cursor[key]++
 // for window w_only: one launch per window keeps the write set (n x 4 B) inside the 126 MB L2, so the
 // random 4-byte stores merge into full sectors before they reach HBM.
-template <int MODE>
+// SL = 32-bit limbs per scalar: 8 (BigInteger256) or 12 (BigInteger384, BW6-761).
+template <int MODE, int SL>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
                                                     uint64_t n, MsmPlan pl, int w_only,
                                                     uint32_t* __restrict__ counts_or_cursor,
                                                     uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         if (inf && inf[i]) continue;
-        const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * 8);
-        uint4 a = __ldg(sp), b = __ldg(sp + 1);
-        uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) continue;
+        const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * SL);
+        uint32_t s[SL];
+        uint32_t any = 0;
+#pragma unroll
+        for (int v = 0; v < SL / 4; v++) {
+            uint4 a = __ldg(sp + v);
+            s[4 * v] = a.x; s[4 * v + 1] = a.y; s[4 * v + 2] = a.z; s[4 * v + 3] = a.w;
+            any |= a.x | a.y | a.z | a.w;
+        }
+        if (any == 0) continue;
         const uint32_t mask = (1u << pl.c) - 1u;
         uint64_t buf = 0;
         int nb = 0, w = 0;
         uint32_t carry = 0;
 #pragma unroll
-        for (int limb = 0; limb <= 8; limb++) {
-            if (limb < 8) {
+        for (int limb = 0; limb <= SL; limb++) {
+            if (limb < SL) {
                 buf |= (uint64_t)s[limb] << nb;
                 nb += 32;
             } else {
@@ -171,7 +178,7 @@ static int windows_for(int scalar_bits, int c) { return (scalar_bits + 1 + c - 1
 
 // precomputed != 0: the windows share one bucket set (bases registered with window multiples)
 static int auto_window_bits(int curve, size_t n, int precomputed) {
-    const int bits = curve == ZKM_CURVE_BLS12_381 ? 255 : 254;
+    const int bits = fr_bits(curve);
     if (n < 2) n = 2;
     double best = 1e300;
     int best_c = 4;
@@ -209,6 +216,8 @@ static const CurveOps* curve_ops(int curve, int group) {
     if (curve == ZKM_CURVE_BLS12_381 && group == 2) return ops_g2_bls();
     if (curve == ZKM_CURVE_BN254 && group == 1) return ops_g1_bn();
     if (curve == ZKM_CURVE_BN254 && group == 2) return ops_g2_bn();
+    if (curve == ZKM_CURVE_BW6_761 && group == 1) return ops_g1_bw6();
+    if (curve == ZKM_CURVE_BW6_761 && group == 2) return ops_g2_bw6();
     ZKM_FAIL(ZKM_ERR_ARG, "unknown curve %d / group %d", curve, group);
 }
 
@@ -318,18 +327,32 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     const unsigned grid_stream = (unsigned)c->sm_count * 8;
     ZKM_CUDA(cudaMemsetAsync(counts, 0, (K + 1) * sizeof(uint32_t), s));
     ZKM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), s));
-    ZKM_LAUNCH(k_msm_digits<0>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
-               (uint32_t*)nullptr, flags);
+    const bool wide = fr_words(curve) == 6;   // 377-bit scalars (BW6-761)
+    if (wide)
+        ZKM_LAUNCH((k_msm_digits<0, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
+                   (uint32_t*)nullptr, flags);
+    else
+        ZKM_LAUNCH((k_msm_digits<0, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
+                   (uint32_t*)nullptr, flags);
     exclusive_scan(c, counts, off, K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(cursor, off, K * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     if (entries * sizeof(uint32_t) <= (96u << 20)) {
         // the whole list array fits in L2: one launch scatters every window
-        ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, cursor,
-                   idx, flags);
+        if (wide)
+            ZKM_LAUNCH((k_msm_digits<1, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1,
+                       cursor, idx, flags);
+        else
+            ZKM_LAUNCH((k_msm_digits<1, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1,
+                       cursor, idx, flags);
     } else {
-        for (int w = 0; w < pl.W; w++)
-            ZKM_LAUNCH(k_msm_digits<1>, grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w, cursor,
-                       idx, flags);
+        for (int w = 0; w < pl.W; w++) {
+            if (wide)
+                ZKM_LAUNCH((k_msm_digits<1, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w,
+                           cursor, idx, flags);
+            else
+                ZKM_LAUNCH((k_msm_digits<1, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w,
+                           cursor, idx, flags);
+        }
     }
 
     mark(1);

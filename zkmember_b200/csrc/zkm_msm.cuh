@@ -76,5 +76,7 @@ const CurveOps* ops_g1_bls();
 const CurveOps* ops_g2_bls();
 const CurveOps* ops_g1_bn();
 const CurveOps* ops_g2_bn();
+const CurveOps* ops_g1_bw6();
+const CurveOps* ops_g2_bw6();
 
 }  // namespace zkm

@@ -143,8 +143,13 @@ k_inv_batch(const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, uint32
     }
 }
 
+// CTAs per SM the unwind kernel is compiled for: 4 (<= 128 registers) for the 256/384-bit fields; the 761-bit
+// field of BW6-761 keeps ~6 coordinates of 24 limbs live and gets 2 (<= 255 registers) instead of spilling.
+template <class F> struct PairBwdMinBlocks { static constexpr int value = 4; };
+template <> struct PairBwdMinBlocks<Bw6_761_Fq> { static constexpr int value = 2; };
+
 template <class F, bool L0>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, PairBwdMinBlocks<F>::value)
 k_pair_bwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off_in,
            const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, const char* __restrict__ pre,
            const char* __restrict__ Tinv, char* __restrict__ dst) {

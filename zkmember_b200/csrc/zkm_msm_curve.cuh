@@ -15,6 +15,11 @@ struct G1Bls { typedef Bls12_381_Fq F; static constexpr int SCALAR_BITS = 255; }
 struct G2Bls { typedef Bls12_381_Fq2 F; static constexpr int SCALAR_BITS = 255; };
 struct G1Bn { typedef Bn254_Fq F; static constexpr int SCALAR_BITS = 254; };
 struct G2Bn { typedef Bn254_Fq2 F; static constexpr int SCALAR_BITS = 254; };
+// BW6-761 (ark-bw6-761 0.3.0; /root/reference/benches/groth16.rs:24-29): G1 (y^2 = x^3 - 1) and G2 (y^2 = x^3 + 4)
+// are both curves over the 761-bit Fq, scalars are 377 bits.  a = 0 and b never enters the group law, so the two
+// groups share every kernel; only the synthetic-base generator differs.
+struct G1Bw6 { typedef Bw6_761_Fq F; static constexpr int SCALAR_BITS = 377; };
+struct G2Bw6 { typedef Bw6_761_Fq F; static constexpr int SCALAR_BITS = 377; };
 
 template <class G> __device__ void load_generator(typename G::F& x, typename G::F& y);
 template <> inline __device__ void load_generator<G1Bls>(Bls12_381_Fq& x, Bls12_381_Fq& y) {
@@ -34,6 +39,13 @@ template <> inline __device__ void load_generator<G2Bn>(Bn254_Fq2& x, Bn254_Fq2&
         x.c0.l[i] = BN254_G2_X0[i]; x.c1.l[i] = BN254_G2_X1[i];
         y.c0.l[i] = BN254_G2_Y0[i]; y.c1.l[i] = BN254_G2_Y1[i];
     }
+}
+
+template <> inline __device__ void load_generator<G1Bw6>(Bw6_761_Fq& x, Bw6_761_Fq& y) {
+    for (int i = 0; i < 24; i++) { x.l[i] = BW6_761_G1_X[i]; y.l[i] = BW6_761_G1_Y[i]; }
+}
+template <> inline __device__ void load_generator<G2Bw6>(Bw6_761_Fq& x, Bw6_761_Fq& y) {
+    for (int i = 0; i < 24; i++) { x.l[i] = BW6_761_G2_X[i]; y.l[i] = BW6_761_G2_Y[i]; }
 }
 
 template <class F>

@@ -45,6 +45,15 @@ template <> struct FrRoots<Bn254_FrP> {
     static __device__ uint32_t two_inv(int i) { return BN254_FR_TWO_INV[i]; }
 };
 
+template <> struct FrRoots<Bw6_761_FrP> {   // 377-bit Fr of BW6-761 = Fq of BLS12-377: GENERATOR = -5, two-adicity 46
+    static constexpr int TWO_ADICITY = BW6_761_FR_TWO_ADICITY;
+    static __device__ uint32_t root(int i) { return BW6_761_FR_ROOT[i]; }
+    static __device__ uint32_t root_inv(int i) { return BW6_761_FR_ROOT_INV[i]; }
+    static __device__ uint32_t gen(int i) { return BW6_761_FR_GEN[i]; }
+    static __device__ uint32_t gen_inv(int i) { return BW6_761_FR_GEN_INV[i]; }
+    static __device__ uint32_t two_inv(int i) { return BW6_761_FR_TWO_INV[i]; }
+};
+
 template <class P>
 __device__ Fp<P> fr_const(uint32_t (*f)(int)) {
     Fp<P> r;
@@ -119,15 +128,19 @@ struct NttPassArgs {
     int coset_lo_bits;
 };
 
-template <int R>
+// NL = 32-bit limbs per element: 8 (255/254-bit Fr) or 12 (377-bit Fr of BW6-761)
+template <int R, int NL>
 struct NttCfg {
     static constexpr int TPT = 1 << (R - 3);               // threads per tile
     static constexpr int NT = TPT > 128 ? TPT : 128;       // threads per CTA
     static constexpr int TILES = NT / TPT;                 // tiles per CTA iteration
-    static constexpr int SMEM = NT * 8 * 32;               // bytes
+    static constexpr int SMEM = NT * 8 * NL * 4;           // bytes
     static constexpr int NR = (R + 2) / 3;                 // register rounds
-    static constexpr int MINB = 512 / NT;                  // 16 warps per SM (<= 128 registers); 8 warps/SM measured 10 % slower
+    // 8 limbs: 16 warps per SM (<= 128 registers); 8 warps/SM measured 10 % slower.  12 limbs: the eight
+    // register-resident elements alone are 96 registers, so 8 warps per SM with up to 255 registers (R <= 11).
+    static constexpr int MINB = NL <= 8 ? 512 / NT : (256 / NT > 0 ? 256 / NT : 1);
 };
+template <class P> struct NttMaxR { static constexpr int value = P::N <= 8 ? 12 : 11; };
 
 __device__ __forceinline__ uint32_t ntt_slot(uint32_t tau, uint32_t q, int pl) {
     return ((tau >> pl) << (pl + 3)) | (q << pl) | (tau & ((1u << pl) - 1u));
@@ -189,13 +202,13 @@ __device__ __forceinline__ Fp<P> coset_factor(const NttPassArgs& a, uint64_t idx
 }
 
 template <class P, int R>
-__global__ void __launch_bounds__(NttCfg<R>::NT, NttCfg<R>::MINB) k_ntt_pass(const NttPassArgs a) {
-    typedef NttCfg<R> C;
+__global__ void __launch_bounds__((NttCfg<R, P::N>::NT), (NttCfg<R, P::N>::MINB)) k_ntt_pass(const NttPassArgs a) {
+    typedef NttCfg<R, P::N> C;
+    constexpr int PLANES = P::N / 4;    // one shared-memory plane per 128-bit quarter of an element
     extern __shared__ uint4 ntt_smem[];
     const uint32_t tl = threadIdx.x / C::TPT;
     const uint32_t tau = threadIdx.x % C::TPT;
-    uint4* sm0 = ntt_smem + (size_t)tl * (2u << R);
-    uint4* sm1 = sm0 + (1u << R);
+    uint4* sm0 = ntt_smem + (size_t)tl * ((uint32_t)PLANES << R);
 
     const int kk = a.k - a.s0;          // log2 n'
     const int logL = kk - R;            // log2 stride
@@ -229,8 +242,10 @@ __global__ void __launch_bounds__(NttCfg<R>::NT, NttCfg<R>::MINB) k_ntt_pass(con
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         uint32_t ph = ntt_phys(ntt_slot(tau, q, plp));
-                        sm0[ph] = make_uint4(x[q].l[0], x[q].l[1], x[q].l[2], x[q].l[3]);
-                        sm1[ph] = make_uint4(x[q].l[4], x[q].l[5], x[q].l[6], x[q].l[7]);
+#pragma unroll
+                        for (int v = 0; v < PLANES; v++)
+                            sm0[((uint32_t)v << R) + ph] =
+                                make_uint4(x[q].l[4 * v], x[q].l[4 * v + 1], x[q].l[4 * v + 2], x[q].l[4 * v + 3]);
                     }
                 }
                 __syncthreads();
@@ -238,9 +253,11 @@ __global__ void __launch_bounds__(NttCfg<R>::NT, NttCfg<R>::MINB) k_ntt_pass(con
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         uint32_t ph = ntt_phys(ntt_slot(tau, q, pl));
-                        uint4 v0 = sm0[ph], v1 = sm1[ph];
-                        x[q].l[0] = v0.x; x[q].l[1] = v0.y; x[q].l[2] = v0.z; x[q].l[3] = v0.w;
-                        x[q].l[4] = v1.x; x[q].l[5] = v1.y; x[q].l[6] = v1.z; x[q].l[7] = v1.w;
+#pragma unroll
+                        for (int v = 0; v < PLANES; v++) {
+                            uint4 t4 = sm0[((uint32_t)v << R) + ph];
+                            x[q].l[4 * v] = t4.x; x[q].l[4 * v + 1] = t4.y; x[q].l[4 * v + 2] = t4.z; x[q].l[4 * v + 3] = t4.w;
+                        }
                     }
                 }
             }
@@ -391,7 +408,7 @@ static void get_coset(Context* c, int curve, int k, int inverse, cudaStream_t s,
 
 template <class P, int R>
 static void launch_pass(Context* c, const NttPassArgs& a, cudaStream_t s) {
-    typedef NttCfg<R> C;
+    typedef NttCfg<R, P::N> C;
     static bool attr_set = false;
     if (!attr_set && C::SMEM > 48 * 1024) {
         ZKM_CUDA(cudaFuncSetAttribute(k_ntt_pass<P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -422,7 +439,9 @@ static void dispatch_pass(Context* c, int R, const NttPassArgs& a, cudaStream_t 
         case 9: launch_pass<P, 9>(c, a, s); break;
         case 10: launch_pass<P, 10>(c, a, s); break;
         case 11: launch_pass<P, 11>(c, a, s); break;
-        case 12: launch_pass<P, 12>(c, a, s); break;
+        case 12:
+            if constexpr (NttMaxR<P>::value >= 12) { launch_pass<P, 12>(c, a, s); break; }
+            [[fallthrough]];
         default: ZKM_FAIL(ZKM_ERR_ARG, "internal: bad NTT radix log %d", R);
     }
 }
@@ -442,7 +461,7 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
     }
     int maxR = c->opt.ntt_max_radix_log;
     if (maxR < 6) maxR = 6;
-    if (maxR > 12) maxR = 12;
+    if (maxR > NttMaxR<P>::value) maxR = NttMaxR<P>::value;
     int passes = (k + maxR - 1) / maxR;
     int Rs[16];
     {   // balanced split, every pass >= 3 stages
@@ -457,16 +476,16 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
     if (passes == 1) {
         if (in == out) {
             work = nullptr;
-            final_dst = (uint32_t*)c->ntt_a.get(n * 32);
+            final_dst = (uint32_t*)c->ntt_a.get(n * P::N * 4);
             copy_back = true;
         }
     } else {
         if (in == out) {
             work = out;  // in-place passes directly on the caller's buffer
-            final_dst = (uint32_t*)c->ntt_a.get(n * 32);
+            final_dst = (uint32_t*)c->ntt_a.get(n * P::N * 4);
             copy_back = true;
         } else {
-            work = (uint32_t*)c->ntt_a.get(n * 32);  // first pass reads `in`, writes scratch
+            work = (uint32_t*)c->ntt_a.get(n * P::N * 4);  // first pass reads `in`, writes scratch
         }
     }
     const uint32_t *clo = nullptr, *chi = nullptr;
@@ -509,7 +528,7 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
         dispatch_pass<P>(c, R, a, s);
         s0 += R;
     }
-    if (copy_back) ZKM_CUDA(cudaMemcpyAsync(out, final_dst, n * 32, cudaMemcpyDeviceToDevice, s));
+    if (copy_back) ZKM_CUDA(cudaMemcpyAsync(out, final_dst, n * P::N * 4, cudaMemcpyDeviceToDevice, s));
 }
 
 // R1CStoQAP::witness_map on device-resident evaluation vectors a, b, c (each 2^k elements, consumed):
@@ -518,7 +537,7 @@ template <class P>
 static void witness_map_t(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n,
                           uint64_t* d_h, cudaStream_t s) {
     const uint64_t n = 1ull << log_n;
-    uint64_t* tmp = (uint64_t*)c->ntt_b.get(n * 32);
+    uint64_t* tmp = (uint64_t*)c->ntt_b.get(n * P::N * 4);
     uint64_t* vecs[3] = {d_a, d_b, d_c};
     for (int v = 0; v < 3; v++) {
         ntt_run_t<P>(c, curve, vecs[v], tmp, log_n, 1, 0, s);   // ifft

@@ -23,7 +23,7 @@ def _curve_id(curve) -> int:
     return _lib.CURVE_IDS[curve] if isinstance(curve, str) else int(curve)
 
 
-TWO_ADICITY = {_lib.CURVE_BLS12_381: 32, _lib.CURVE_BN254: 28}
+TWO_ADICITY = {_lib.CURVE_BLS12_381: 32, _lib.CURVE_BN254: 28, _lib.CURVE_BW6_761: 46}
 
 
 class Radix2EvaluationDomain:
@@ -31,7 +31,8 @@ class Radix2EvaluationDomain:
         self.curve = _curve_id(curve)
         self.log_size_of_group = int(log_size_of_group)
         self.size = 1 << self.log_size_of_group
-        consts = np.zeros((5, 4), dtype=np.uint64)
+        self.words = _lib.FR_WORDS[self.curve]
+        consts = np.zeros((5, self.words), dtype=np.uint64)
         _lib.check(_lib.lib().zkm_domain_constants(self.curve, self.log_size_of_group,
                                                    ctypes.c_void_p(consts.ctypes.data)))
         self.group_gen, self.group_gen_inv, self.size_inv, self.generator, self.generator_inv = (
@@ -49,16 +50,16 @@ class Radix2EvaluationDomain:
 
     # -- helpers
     def _prepare(self, x) -> np.ndarray:
-        a = np.array(x, dtype=np.uint64, order="C").reshape(-1, 4)
+        a = np.array(x, dtype=np.uint64, order="C").reshape(-1, self.words)
         if len(a) > self.size:
             raise ValueError("input of %d elements exceeds the domain size %d" % (len(a), self.size))
         if len(a) < self.size:  # upstream: coeffs.resize(self.size(), zero)
-            a = np.concatenate([a, np.zeros((self.size - len(a), 4), dtype=np.uint64)])
+            a = np.concatenate([a, np.zeros((self.size - len(a), self.words), dtype=np.uint64)])
         return a
 
     def _run_in_place(self, a: np.ndarray, inverse: bool, coset: bool):
-        if a.dtype != np.uint64 or not a.flags["C_CONTIGUOUS"] or a.size != 4 * self.size:
-            raise ValueError("in-place transforms need a C-contiguous uint64 array of exactly size x 4 words")
+        if a.dtype != np.uint64 or not a.flags["C_CONTIGUOUS"] or a.size != self.words * self.size:
+            raise ValueError("in-place transforms need a C-contiguous uint64 array of exactly size x %d words" % self.words)
         _lib.check(_lib.lib().zkm_ntt(self.curve, ctypes.c_void_p(a.ctypes.data), self.log_size_of_group,
                                       int(inverse), int(coset)))
 

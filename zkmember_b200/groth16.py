@@ -23,9 +23,10 @@ def witness_map(a, b, c, curve="bls12_381") -> np.ndarray:
     """h = coset_ifft((coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / (g^n - 1)).
     a, b, c: (n, 4) uint64 Montgomery evaluations over the domain, n a power of two."""
     cid = _curve_id(curve)
-    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
-    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
-    c = np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4)
+    S = _lib.FR_WORDS[cid]
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, S)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, S)
+    c = np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, S)
     n = len(a)
     log_n = n.bit_length() - 1
     if n == 0 or (1 << log_n) != n or len(b) != n or len(c) != n:

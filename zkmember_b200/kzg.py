@@ -32,7 +32,7 @@ class KZG10:
     @staticmethod
     def commit(powers: RegisteredBases, coeffs) -> AffinePoint:
         """coeffs: (d + 1, 4) uint64 Montgomery Fr, low degree first (DensePolynomial::coeffs)."""
-        c = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+        c = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, _lib.FR_WORDS[powers.curve])
         if len(c) > powers.n:
             raise ValueError("polynomial degree %d exceeds the %d registered powers" % (len(c) - 1, powers.n))
         W = coord_words(powers.curve, 1)

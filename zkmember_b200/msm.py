@@ -20,10 +20,14 @@ import numpy as np
 
 from . import _lib
 
-L64 = {_lib.CURVE_BLS12_381: 6, _lib.CURVE_BN254: 4}
+L64 = {_lib.CURVE_BLS12_381: 6, _lib.CURVE_BN254: 4, _lib.CURVE_BW6_761: 12}
+FR_WORDS = _lib.FR_WORDS
 
 
 def coord_words(curve: int, group: int) -> int:
+    """u64 words per coordinate: Fq (G1) or Fq2 (G2); BW6-761's G2 is a curve over Fq as well."""
+    if curve == _lib.CURVE_BW6_761:
+        return L64[curve]
     return L64[curve] * (2 if group == 2 else 1)
 
 
@@ -95,7 +99,7 @@ class RegisteredBases:
             self.handle = 0
 
     def msm(self, scalars, offset: int = 0, n: int | None = None) -> AffinePoint:
-        s = _as_u64(scalars, 4, "scalars")
+        s = _as_u64(scalars, FR_WORDS[cid], "scalars")
         avail = self.n - offset
         n = min(len(s), avail) if n is None else n
         W = coord_words(self.curve, self.group)
@@ -118,7 +122,7 @@ class VariableBaseMSM:
         cid = _curve_id(curve)
         W = coord_words(cid, group)
         b = _as_u64(bases, 2 * W, "bases")
-        s = _as_u64(scalars, 4, "scalars")
+        s = _as_u64(scalars, FR_WORDS[cid], "scalars")
         n = min(len(b), len(s))          # upstream: size = min(bases.len(), scalars.len())
         inf = None
         if infinity is not None:
