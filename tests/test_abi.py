@@ -75,7 +75,8 @@ def test_domain_new_mirrors_upstream_size_rules():
     # new() returns None above the two-adicity without touching the GPU
     assert Radix2EvaluationDomain.new((1 << 28) + 1, "bn254") is None
     assert Radix2EvaluationDomain.new((1 << 32) + 1, "bls12_381") is None
-    assert TWO_ADICITY == {0: 32, 1: 28}
+    assert Radix2EvaluationDomain.new((1 << 46) + 1, "bw6_761") is None
+    assert TWO_ADICITY == {0: 32, 1: 28, 2: 46}
 
 
 def test_window_bits_heuristic_is_monotone():
