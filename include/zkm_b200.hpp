@@ -11,7 +11,7 @@
 //   zkm::ProvingKeyBases / KZG10::commit                        registered bases (pk / SRS reuse)
 //
 // Types are plain structs with arkworks' memory layout: Fp256 = 4 x u64 Montgomery limbs, Fp384 = 6,
-// BigInteger256 = 4 x u64 canonical limbs, GroupAffine{x, y, infinity}.  Errors of the C ABI become
+// BigInteger256 = 4 x u64 canonical limbs (BigInteger384 = 6 for BW6-761), GroupAffine{x, y, infinity}.  Errors of the C ABI become
 // zkm::Error exceptions (upstream's functions are infallible; there is no CPU fallback to hide behind).
 #pragma once
 #include <algorithm>
@@ -41,9 +41,12 @@ struct Fp {
     uint64_t limbs[L64];  // Montgomery form, little-endian limbs (ark-ff Fp256 / Fp384)
     bool operator==(const Fp& o) const { return std::memcmp(limbs, o.limbs, sizeof(limbs)) == 0; }
 };
-struct BigInteger256 {
-    uint64_t limbs[4];    // canonical integer (Fr::into_repr())
+template <int L64>
+struct BigInteger {
+    uint64_t limbs[L64];  // canonical integer (Fr::into_repr())
 };
+typedef BigInteger<4> BigInteger256;
+typedef BigInteger<6> BigInteger384;   // scalars of BW6-761 (377-bit Fr)
 template <int L64>
 struct Fp2 {
     Fp<L64> c0, c1;
@@ -54,18 +57,32 @@ struct Bls12_381 {
     static constexpr int TWO_ADICITY = 32;
     typedef Fp<4> Fr;
     typedef Fp<6> Fq;
+    typedef Fp2<6> G2Coord;
+    typedef BigInteger256 BigInt;
 };
 struct Bn254 {
     static constexpr int ID = ZKM_CURVE_BN254;
     static constexpr int TWO_ADICITY = 28;
     typedef Fp<4> Fr;
     typedef Fp<4> Fq;
+    typedef Fp2<4> G2Coord;
+    typedef BigInteger256 BigInt;
+};
+// The second curve zkMember instantiates (/root/reference/benches/groth16.rs:24-29): 761-bit Fq, 377-bit Fr
+// (= the base field of BLS12-377), and a G2 that is a curve over Fq itself.
+struct Bw6_761 {
+    static constexpr int ID = ZKM_CURVE_BW6_761;
+    static constexpr int TWO_ADICITY = 46;
+    typedef Fp<6> Fr;
+    typedef Fp<12> Fq;
+    typedef Fp<12> G2Coord;
+    typedef BigInteger384 BigInt;
 };
 
-// GroupAffine<P>: x, y, infinity.  G1: Coord = Fq; G2: Coord = Fp2<Fq limbs>.
+// GroupAffine<P>: x, y, infinity.  G1: Coord = Fq; G2: Coord = Fp2<Fq limbs> (BW6-761: Fq).
 template <class Curve, int GROUP>
 struct GroupAffine {
-    typedef typename std::conditional<GROUP == 1, typename Curve::Fq, Fp2<sizeof(typename Curve::Fq) / 8>>::type Coord;
+    typedef typename std::conditional<GROUP == 1, typename Curve::Fq, typename Curve::G2Coord>::type Coord;
     Coord x, y;
     bool infinity = false;
     bool operator==(const GroupAffine& o) const {
@@ -119,7 +136,7 @@ public:
     size_t size() const { return n_; }
     uint64_t handle() const { return handle_; }
     // sum over min(size() - offset, scalars.size()) pairs starting at bases[offset]
-    GroupAffine<Curve, GROUP> msm(const std::vector<BigInteger256>& scalars, size_t offset = 0) const {
+    GroupAffine<Curve, GROUP> msm(const std::vector<typename Curve::BigInt>& scalars, size_t offset = 0) const {
         size_t n = std::min(scalars.size(), n_ - std::min(offset, n_));
         typedef typename GroupAffine<Curve, GROUP>::Coord Coord;
         std::vector<uint64_t> out(2 * sizeof(Coord) / 8);
@@ -138,7 +155,7 @@ struct VariableBaseMSM {
     // ark_ec::msm::VariableBaseMSM::multi_scalar_mul followed by into_affine()
     template <class Curve, int GROUP>
     static GroupAffine<Curve, GROUP> multi_scalar_mul(const std::vector<GroupAffine<Curve, GROUP>>& bases,
-                                                      const std::vector<BigInteger256>& scalars) {
+                                                      const std::vector<typename Curve::BigInt>& scalars) {
         typedef typename GroupAffine<Curve, GROUP>::Coord Coord;
         const size_t size = std::min(bases.size(), scalars.size());   // upstream: min(bases.len(), scalars.len())
         std::vector<uint64_t> xy;
@@ -171,12 +188,13 @@ public:
         Radix2EvaluationDomain d;
         d.size = uint64_t(1) << log_n;
         d.log_size_of_group = log_n;
-        uint64_t c[5 * 4];
+        constexpr size_t S = sizeof(F) / 8;
+        uint64_t c[5 * S];
         check(zkm_domain_constants(Curve::ID, log_n, c), "zkm_domain_constants");
-        std::memcpy(&d.group_gen, c, 32);
-        std::memcpy(&d.group_gen_inv, c + 4, 32);
-        std::memcpy(&d.size_inv, c + 8, 32);
-        std::memcpy(&d.generator_inv, c + 16, 32);
+        std::memcpy(&d.group_gen, c, sizeof(F));
+        std::memcpy(&d.group_gen_inv, c + S, sizeof(F));
+        std::memcpy(&d.size_inv, c + 2 * S, sizeof(F));
+        std::memcpy(&d.generator_inv, c + 4 * S, sizeof(F));
         return d;
     }
     void fft_in_place(std::vector<F>& coeffs) const { run(coeffs, 0, 0); }

@@ -42,8 +42,8 @@ static bool run_msm(size_t n, const std::vector<uint8_t>& bases, const std::vect
         std::memcpy(&b[i].y, bases.data() + i * 2 * sizeof(Coord) + sizeof(Coord), sizeof(Coord));
         b[i].infinity = inf[i] != 0;
     }
-    std::vector<zkm::BigInteger256> s(n);
-    if (n) std::memcpy(s.data(), scal.data(), n * 32);
+    std::vector<typename Curve::BigInt> s(n);
+    if (n) std::memcpy(s.data(), scal.data(), n * sizeof(typename Curve::BigInt));
     A r = zkm::VariableBaseMSM::multi_scalar_mul<Curve, GROUP>(b, s);
     bool ok = (int)r.infinity == want_inf && std::memcmp(&r.x, want.data(), sizeof(Coord)) == 0 &&
               std::memcmp(&r.y, want.data() + sizeof(Coord), sizeof(Coord)) == 0;
@@ -62,11 +62,11 @@ static bool run_wmap(int log_n, const std::vector<uint8_t>& a, const std::vector
     auto dom = zkm::Radix2EvaluationDomain<Curve>::new_(size_t(1) << log_n);
     size_t n = size_t(1) << log_n;
     std::vector<F> va(n), vb(n), vc(n);
-    std::memcpy(va.data(), a.data(), n * 32);
-    std::memcpy(vb.data(), b.data(), n * 32);
-    std::memcpy(vc.data(), c.data(), n * 32);
+    std::memcpy(va.data(), a.data(), n * sizeof(F));
+    std::memcpy(vb.data(), b.data(), n * sizeof(F));
+    std::memcpy(vc.data(), c.data(), n * sizeof(F));
     std::vector<F> h = zkm::witness_map(*dom, va, vb, vc);
-    return std::memcmp(h.data(), want.data(), n * 32) == 0;
+    return std::memcmp(h.data(), want.data(), n * sizeof(F)) == 0;
 }
 
 int main(int argc, char** argv) {
@@ -92,18 +92,21 @@ int main(int argc, char** argv) {
                 int log_n, inv, cos; std::string hin, hout;
                 is >> log_n >> inv >> cos >> hin >> hout;
                 ok = curve == "bls12_381" ? run_ntt<zkm::Bls12_381>(log_n, inv, cos, unhex(hin), unhex(hout))
-                                          : run_ntt<zkm::Bn254>(log_n, inv, cos, unhex(hin), unhex(hout));
+                     : curve == "bn254"   ? run_ntt<zkm::Bn254>(log_n, inv, cos, unhex(hin), unhex(hout))
+                                          : run_ntt<zkm::Bw6_761>(log_n, inv, cos, unhex(hin), unhex(hout));
             } else if (kind == "msm") {
                 int group, rinf; size_t n; std::string hb, hi, hs, hr;
                 is >> group >> n >> hb >> hi >> hs >> hr >> rinf;
                 auto B = unhex(hb), I = unhex(hi), S = unhex(hs), R = unhex(hr);
                 if (curve == "bls12_381") ok = group == 1 ? run_msm<zkm::Bls12_381, 1>(n, B, I, S, R, rinf) : run_msm<zkm::Bls12_381, 2>(n, B, I, S, R, rinf);
-                else ok = group == 1 ? run_msm<zkm::Bn254, 1>(n, B, I, S, R, rinf) : run_msm<zkm::Bn254, 2>(n, B, I, S, R, rinf);
+                else if (curve == "bn254") ok = group == 1 ? run_msm<zkm::Bn254, 1>(n, B, I, S, R, rinf) : run_msm<zkm::Bn254, 2>(n, B, I, S, R, rinf);
+                else ok = group == 1 ? run_msm<zkm::Bw6_761, 1>(n, B, I, S, R, rinf) : run_msm<zkm::Bw6_761, 2>(n, B, I, S, R, rinf);
             } else if (kind == "wmap") {
                 int log_n; std::string ha, hb, hc, hh;
                 is >> log_n >> ha >> hb >> hc >> hh;
                 ok = curve == "bls12_381" ? run_wmap<zkm::Bls12_381>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh))
-                                          : run_wmap<zkm::Bn254>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh));
+                     : curve == "bn254"   ? run_wmap<zkm::Bn254>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh))
+                                          : run_wmap<zkm::Bw6_761>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh));
             } else {
                 continue;
             }

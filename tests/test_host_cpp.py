@@ -34,7 +34,7 @@ def _vectors(path):
         inf = bytes(v["infinity"]).hex() or "-"
         lines.append("msm %s %d %d %s %s %s %s %d" % (v["curve"], v["group"], v["n"], v["bases"] or "-", inf, v["scalars"] or "-",
                                                          v["result"], v["result_infinity"]))
-    for cid, name in ((0, "bls12_381"), (1, "bn254")):
+    for cid, name in ((0, "bls12_381"), (1, "bn254"), (2, "bw6_761")):
         n = 1 << 9
         a, b, c = (capi.random_field_elements(cid, n, seed=s) for s in (21, 22, 23))
         h = capi.witness_map(cid, a, b, c)

@@ -43,10 +43,12 @@ ap.add_argument("--curve", default="bls12_381")
 ap.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")))
 args = ap.parse_args()
 
-cid = {"bls12_381": 0, "bn254": 1}[args.curve]
+cid = {"bls12_381": 0, "bn254": 1, "bw6_761": 2}[args.curve]
 log_n = args.log_n
 n = 1 << log_n
-W1 = 6 if cid == 0 else 4
+W1 = capi.coord_words(cid, 1)          # u64 words per G1 coordinate
+W2 = capi.coord_words(cid, 2)          # ... per G2 coordinate (BW6-761: G2 is over Fq too)
+SW = capi.fr_words(cid)                # u64 words per Fr element / scalar
 torch.cuda.set_device(args.device)
 zkm.init(args.device)
 L = _lib.lib()
@@ -86,16 +88,16 @@ class Pipeline:
         self.st = torch.cuda.Stream(device=dev)
         self.msm_streams = {k: torch.cuda.Stream(device=dev) for k in KEYS}
         self.pool = ThreadPoolExecutor(max_workers=5)
-        self.d_abc = torch.empty((3, n, 4), dtype=torch.int64, device=dev)
-        self.d_h = torch.empty((n, 4), dtype=torch.int64, device=dev)
-        self.d_full = torch.empty((n, 4), dtype=torch.int64, device=dev)
-        self.recs = {k: torch.zeros((4 * W1 + 1) if k == "b_g2" else (2 * W1 + 1), dtype=torch.int64, device=dev) for k in KEYS}
+        self.d_abc = torch.empty((3, n, SW), dtype=torch.int64, device=dev)
+        self.d_h = torch.empty((n, SW), dtype=torch.int64, device=dev)
+        self.d_full = torch.empty((n, SW), dtype=torch.int64, device=dev)
+        self.recs = {k: torch.zeros((2 * W2 + 1) if k == "b_g2" else (2 * W1 + 1), dtype=torch.int64, device=dev) for k in KEYS}
         self.h_recs = {k: torch.zeros_like(v, device="cpu").pin_memory() for k, v in self.recs.items()}
 
     def _msm(self, k, stream_handle):
         ptr, cnt = {
             "h": (self.d_h.data_ptr(), sizes["h"]),
-            "l": (self.d_full.data_ptr() + 32 * (n - sizes["l"]), sizes["l"]),
+            "l": (self.d_full.data_ptr() + 8 * SW * (n - sizes["l"]), sizes["l"]),
             "a": (self.d_full.data_ptr(), sizes["a"]),
             "b_g1": (self.d_full.data_ptr(), sizes["b_g1"]),
             "b_g2": (self.d_full.data_ptr(), sizes["b_g2"]),
@@ -124,7 +126,7 @@ class Pipeline:
             elif not args.python_threads:
                 # one C call: the library runs the five MSMs on five lanes / host threads of its own
                 from zkmember_b200.msm import msm_batch_device
-                src = {"h": (self.d_h.data_ptr(), sizes["h"]), "l": (self.d_full.data_ptr() + 32 * (n - sizes["l"]), sizes["l"]),
+                src = {"h": (self.d_h.data_ptr(), sizes["h"]), "l": (self.d_full.data_ptr() + 8 * SW * (n - sizes["l"]), sizes["l"]),
                        "a": (self.d_full.data_ptr(), sizes["a"]), "b_g1": (self.d_full.data_ptr(), sizes["b_g1"]),
                        "b_g2": (self.d_full.data_ptr(), sizes["b_g2"])}
                 msm_batch_device([(regs[k], src[k][0], src[k][1], self.recs[k].data_ptr()) for k in ("b_g2", "h", "l", "a", "b_g1")],
@@ -173,7 +175,7 @@ launches = _lib.launch_count() // total
 out = {"op": "groth16_proxy", "curve": args.curve, "log_n": log_n, "precompute": not args.no_precompute,
        "concurrent_msms": not args.serial, "proofs_in_flight": len(pipes), "proofs_timed": total,
        "ms_per_proof": wall * 1e3, "proofs_per_s": 1.0 / wall, "kernel_launches_per_proof": int(launches),
-       "pk_register_s": reg_s, "h2d_bytes_per_proof": int(4 * n * 32),
+       "pk_register_s": reg_s, "h2d_bytes_per_proof": int(4 * n * 8 * SW),
        "d2h_bytes_per_proof": int(8 * (4 * (2 * W1 + 1) + 4 * W1 + 1)),
        "note": "MSM + NTT portion of create_proof only (no R1CS synthesis); synthetic zkMember-shaped sizes"}
 
@@ -198,12 +200,12 @@ if args.cpu:
     # h: the witness-map output is compared element-wise; its MSM (dense scalars) is checked through
     # into_repr of the oracle's h and the oracle MSM
     h_repr = np.zeros_like(hh)
-    fid = 1 if cid == 0 else 3
+    fid = {0: 1, 1: 3, 2: 5}[cid]
     for i in range(0, n, max(1, n // 64)):   # spot-check into_repr on 64 elements with the oracle field op
         h_repr[i] = capi.field_op(fid, 4, hh[i])
     with torch.cuda.stream(P.st):
         P.d_abc[0].copy_(h_a); P.d_abc[1].copy_(h_b); P.d_abc[2].copy_(h_c)
-        d_chk = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        d_chk = torch.empty((n, SW), dtype=torch.int64, device=dev)
         sp = ctypes.c_void_p(P.st.cuda_stream)
         _lib.check(L.zkm_witness_map_device(cid, ctypes.c_void_p(P.d_abc[0].data_ptr()), ctypes.c_void_p(P.d_abc[1].data_ptr()),
                                             ctypes.c_void_p(P.d_abc[2].data_ptr()), log_n, ctypes.c_void_p(d_chk.data_ptr()), sp))

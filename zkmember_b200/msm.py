@@ -99,7 +99,7 @@ class RegisteredBases:
             self.handle = 0
 
     def msm(self, scalars, offset: int = 0, n: int | None = None) -> AffinePoint:
-        s = _as_u64(scalars, FR_WORDS[cid], "scalars")
+        s = _as_u64(scalars, FR_WORDS[self.curve], "scalars")
         avail = self.n - offset
         n = min(len(s), avail) if n is None else n
         W = coord_words(self.curve, self.group)
