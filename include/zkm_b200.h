@@ -152,7 +152,9 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
  * "ntt_max_radix_log" (6..12), "profile" (0 | 1), "msm_precompute" (0 | 1: bases registered while it is
  * set also store their window multiples 2^(c w) P -- W times the memory, one-time cost -- so that all
  * windows of later MSMs share one bucket set and the final doubling chain disappears; meant for proving
- * keys / SRS that are reused across many proofs).  Unknown keys fail with ZKM_ERR_ARG. */
+ * keys / SRS that are reused across many proofs), "msm_xarr" (0 | 1: level-0 x-coordinate array, default 1),
+ * "msm_prefetch_fwd" / "msm_prefetch_bwd" (L2 prefetch distance of the level-0 gathers, default 0 = off).
+ * Unknown keys fail with ZKM_ERR_ARG. */
 int32_t zkm_set_option(const char* key, int64_t value);
 /* With option "profile" = 1: device time (ms, CUDA events on the launching stream) of the six stages of
  * the last MSM: bucket sort | batched-affine pair levels | task lists | XYZZ bucket accumulation | folds |

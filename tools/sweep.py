@@ -29,11 +29,15 @@ ap.add_argument("--max", type=int, default=24)
 ap.add_argument("--kind", default="uniform")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--precompute", action="store_true")
+ap.add_argument("--opt", action="append", default=[], help="library option key=value (zkm_set_option), repeatable")
 ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle (arkworks algorithm restated) up to 2^20")
 args = ap.parse_args()
 
 cid = {"bls12_381": 0, "bn254": 1, "bw6_761": 2}[args.curve]
 zkm.init(0)
+for kv in args.opt:
+    k_, v_ = kv.split("=")
+    zkm.set_option(k_, int(v_))
 L = _lib.lib()
 dev = torch.device("cuda:0")
 st = torch.cuda.Stream()
@@ -88,6 +92,8 @@ if args.what == "msm":
             capi.msm(cid, args.group, hb, h)
             row["cpu_ms"] = (time.perf_counter() - t0) * 1e3
         row["precompute"] = bool(args.precompute)
+        if args.opt:
+            row["opts"] = args.opt
         reg.release()
         print(json.dumps(row), flush=True)
 else:

@@ -547,6 +547,11 @@ int32_t zkm_set_option(const char* key, int64_t value) {
         } else if (!strcmp(key, "msm_pair_m2")) {
             if (value < 2 || value > 4096) ZKM_FAIL(ZKM_ERR_ARG, "msm_pair_m2 must be 2..4096");
             c->opt.msm_pair_m2 = (int)value;
+        } else if (!strcmp(key, "msm_prefetch_fwd") || !strcmp(key, "msm_prefetch_bwd")) {
+            if (value < 0 || value > 64) ZKM_FAIL(ZKM_ERR_ARG, "%s must be 0 (off) .. 64 pairs ahead", key);
+            (key[13] == 'f' ? c->opt.msm_prefetch_fwd : c->opt.msm_prefetch_bwd) = (int)value;
+        } else if (!strcmp(key, "msm_xarr")) {
+            c->opt.msm_xarr = value ? 1 : 0;
         } else if (!strcmp(key, "msm_fold")) {
             if (value != 0 && (value < 2 || value > 1024)) ZKM_FAIL(ZKM_ERR_ARG, "msm_fold must be 0 (auto) or 2..1024");
             c->opt.msm_fold = (int)value;

@@ -109,6 +109,11 @@ struct Options {
     int msm_precompute = 0;  // registrations made while set carry precomputed window multiples
     int msm_affine_levels = -1;  // batched-affine pairwise levels before the XYZZ tasks (-1 = automatic)
     int msm_pair_m = 64, msm_pair_m2 = 32;  // outputs per thread / totals per inversion thread in the pair levels
+    // L2 prefetch distance (pairs ahead) of the level-0 gathers; 0 = off.  Measured on B200 at 2^24: every setting
+    // > 0 is SLOWER (+10 ms each for fwd and bwd): the level-0 passes are bound by random-access DRAM throughput,
+    // not by latency, and the prefetches add traffic.  Kept as a knob, off by default.
+    int msm_prefetch_fwd = 0, msm_prefetch_bwd = 0;
+    int msm_xarr = 1;            // level-0 forward pass gathers x from an array of 64-byte slots (48-byte coordinates)
     int msm_fold = 0;            // fan-in of the XYZZ fold levels (0 = automatic: 4 for small MSMs, 16 for large)
 };
 

@@ -224,7 +224,7 @@ static const CurveOps* curve_ops(int curve, int group) {
 enum WsSlot {
     WS_COUNTS = 0, WS_OFF, WS_CURSOR, WS_IDX, WS_TPB_A, WS_TBASE_A, WS_TPB_B, WS_TBASE_B, WS_TSTART, WS_TLEN,
     WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_PART_B, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP,
-    WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2
+    WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2, WS_XARR
 };
 
 static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t count, cudaStream_t s) {
@@ -378,6 +378,14 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         const uint32_t m = (uint32_t)c->opt.msm_pair_m, m2 = (uint32_t)c->opt.msm_pair_m2;
         size_t Eb = entries;
         int p = 0;
+        // x coordinates of the bases in 64-byte slots for the level-0 forward gathers (one DRAM burst per x);
+        // rebuilt per call (2.5 GB of streaming traffic at 2^24, ~0.4 ms) -- not for tables of window multiples
+        const void* xarr = nullptr;
+        if (n_aff > 0 && ops->xarr_slot > 0 && !use_pre && c->opt.msm_xarr) {
+            void* xa = c->ws[WS_XARR].get(n * (size_t)ops->xarr_slot);
+            ops->build_xarr((unsigned)c->sm_count, s, d_bases, (uint64_t)n, xa);
+            xarr = xa;
+        }
         for (int lvl = 0; lvl < n_aff; lvl++) {
             const size_t Eout = (Eb + (K < Eb ? K : Eb)) / 2 + 1;      // bound on the outputs of this level
             const size_t nT = (Eout + m - 1) / m, nU = (nT + m2 - 1) / m2;
@@ -389,9 +397,10 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
             char* pre2 = (char*)c->ws[WS_PRE2].get((nT + 1) * CBy);
             ZKM_LAUNCH(k_pair_lens, kblocks, 256, 0, s, cur_off, K, alen);
             exclusive_scan(c, alen, aoff, K + 1, s);
-            ops->pair_fwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt);
+            ops->pair_fwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt,
+                          c->opt.msm_prefetch_fwd, lvl == 0 ? xarr : nullptr);
             ops->pair_inv((unsigned)c->sm_count, nU, s, aoff, K, m, m2, Tt, pre2);
-            ops->pair_bwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt, pt);
+            ops->pair_bwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt, pt, c->opt.msm_prefetch_bwd);
             cur_off = aoff;
             cur_cnt = alen;
             cur_src = pt;

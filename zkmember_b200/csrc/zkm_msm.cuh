@@ -50,12 +50,16 @@ struct CurveOps {
     // batched-affine pairwise level (zkm_msm_affine.cuh): denominators + prefix products, inversion of the
     // per-thread totals, unwind + affine additions into the next level's array
     void (*pair_fwd)(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                     const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T);
+                     const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, int pf,
+                     const void* xarr);
+    // level-0 x-coordinate array (xarr_slot bytes per base; 0 = this group does not use one)
+    void (*build_xarr)(unsigned sm_count, cudaStream_t s, const void* bases, uint64_t n, void* xarr);
+    int xarr_slot;
     void (*pair_inv)(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
                      uint32_t m2, void* T, void* pre2);
     void (*pair_bwd)(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
                      const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
-                     void* dst);
+                     void* dst, int pf);
     size_t coord_bytes;
 };
 

@@ -49,6 +49,13 @@ __device__ __forceinline__ const char* pair_src(const char* src, const uint32_t*
     return src + (size_t)i * (2 * CB);
 }
 
+// Level 0 gathers whole base records at random: ask L2 for the records a few pairs ahead of the one being
+// worked on (no registers held, unlike a software pipeline), so the dependent-product chain of the thread
+// finds them in L2 instead of waiting out a DRAM round trip.  `bytes` = 48/96/... rounded up to 32-byte sectors.
+__device__ __forceinline__ void prefetch_l2(const char* p, int bytes) {
+    for (int o = 0; o < bytes; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
 struct PairCursor {  // bucket of the current output element
     uint32_t k, lo, hi;
 };
@@ -72,12 +79,30 @@ struct PairKind {
     bool inf0, inf1;
 };
 
+// Level 0 of the forward pass only needs the x coordinates.  A 48-byte x inside a 96-byte record that is merely
+// 32-byte aligned straddles two 64-byte DRAM bursts half of the time (ncu: 29 GB read for 14 GB of x); gathered
+// from a separate array of 64-byte-aligned slots every x costs exactly one burst.  XSLOT = 0: no such array.
+template <class F> struct XArr { static constexpr int SLOT = (CoordIO<F>::BYTES == 48) ? 64 : 0; };
+
+template <class F>
+__global__ void __launch_bounds__(256) k_build_xarr(const char* __restrict__ bases, uint64_t n, char* __restrict__ xarr) {
+    constexpr int CB = CoordIO<F>::BYTES;
+    constexpr int SLOT = XArr<F>::SLOT > 0 ? XArr<F>::SLOT : CB;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        CoordIO<F>::st(xarr + i * SLOT, CoordIO<F>::ld(bases + i * 2 * CB));
+}
+
 template <class F, bool L0>
 __global__ void __launch_bounds__(256)
 k_pair_fwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off_in,
-           const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, char* __restrict__ pre, char* __restrict__ T) {
+           const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, char* __restrict__ pre, char* __restrict__ T, int pf,
+           const char* __restrict__ xarr) {
     constexpr int CB = CoordIO<F>::BYTES;
+    constexpr int XS = XArr<F>::SLOT > 0 ? XArr<F>::SLOT : 2 * CB;
     const uint32_t E = off_out[K];
+    uint32_t Ein = 0;
+    if (L0) Ein = off_in[K];
+    const bool use_x = L0 && XArr<F>::SLOT > 0 && xarr != nullptr;
     const uint32_t nT = (E + m - 1) / m;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nT; t += gridDim.x * blockDim.x) {
         const uint32_t e0 = t * m, e1 = (e0 + m < E) ? e0 + m : E;
@@ -94,13 +119,26 @@ k_pair_fwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const
                 ie = off_in[c.k + 1];
             }
             const uint32_t i0 = ib + 2 * (e - c.lo);
+            if (L0 && pf > 0) {   // x coordinates of the pair `pf` outputs ahead (list positions advance by ~2 per output)
+                const uint32_t pi = i0 + 2 * (uint32_t)pf;
+                if (pi + 1 < Ein) {
+                    prefetch_l2(src + (size_t)(idx[pi] & 0x7fffffffu) * (2 * CB), CB);
+                    prefetch_l2(src + (size_t)(idx[pi + 1] & 0x7fffffffu) * (2 * CB), CB);
+                }
+            }
             CoordIO<F>::st(pre + (size_t)e * CB, run);
             if (i0 + 1 < ie) {
                 uint32_t s0, s1;
                 const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
                 const char* p1 = pair_src<F, L0>(src, idx, i0 + 1, s1);
-                F x0 = L0 ? CoordIO<F>::ld_gather(p0) : CoordIO<F>::ld_plain(p0);
-                F x1 = L0 ? CoordIO<F>::ld_gather(p1) : CoordIO<F>::ld_plain(p1);
+                F x0, x1;
+                if (use_x) {
+                    x0 = CoordIO<F>::ld_gather(xarr + (size_t)(idx[i0] & 0x7fffffffu) * XS);
+                    x1 = CoordIO<F>::ld_gather(xarr + (size_t)(idx[i0 + 1] & 0x7fffffffu) * XS);
+                } else {
+                    x0 = L0 ? CoordIO<F>::ld_gather(p0) : CoordIO<F>::ld_plain(p0);
+                    x1 = L0 ? CoordIO<F>::ld_gather(p1) : CoordIO<F>::ld_plain(p1);
+                }
                 if (!aff_is_identity(x0) && !aff_is_identity(x1)) {
                     if (x0 != x1) {
                         run = run * (x1 - x0);
@@ -152,7 +190,7 @@ template <class F, bool L0>
 __global__ void __launch_bounds__(128, PairBwdMinBlocks<F>::value)
 k_pair_bwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off_in,
            const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, const char* __restrict__ pre,
-           const char* __restrict__ Tinv, char* __restrict__ dst) {
+           const char* __restrict__ Tinv, char* __restrict__ dst, int pf) {
     constexpr int CB = CoordIO<F>::BYTES;
     const uint32_t E = off_out[K];
     const uint32_t nT = (E + m - 1) / m;
@@ -171,6 +209,11 @@ k_pair_bwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const
                 ib = off_in[c.k];
             }
             const uint32_t i0 = ib + 2 * (e - c.lo);
+            if (L0 && pf > 0 && i0 >= 2 * (uint32_t)pf) {   // the walk is backwards: whole records (x, y) of an earlier pair
+                const uint32_t pi = i0 - 2 * (uint32_t)pf;
+                prefetch_l2(src + (size_t)(idx[pi] & 0x7fffffffu) * (2 * CB), 2 * CB);
+                prefetch_l2(src + (size_t)(idx[pi + 1] & 0x7fffffffu) * (2 * CB), 2 * CB);
+            }
             uint32_t s0, s1;
             const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
             F x0 = L0 ? CoordIO<F>::ld_gather(p0) : CoordIO<F>::ld_plain(p0);

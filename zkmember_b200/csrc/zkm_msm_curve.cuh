@@ -166,14 +166,42 @@ k_bucket_reduce(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ 
     if (gid >= W * per_w) return;
     const uint32_t w = gid / per_w, t = gid % per_w;
     const uint32_t lo = t * g;
-    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
-    for (uint32_t b = lo + g; b-- > lo;) {
-        const uint32_t k = w * B + b;
-        if (cnt[k]) {
-            XYZZ<F> S = ld_xyzz(items + off[k]);
-            add_sel(run, S);
+    XYZZ<F> run, acc;
+    if (InlineLaw<F>::value) {
+        // ONE inlined addition site for both `run += S` and `acc += run`: two inlined copies of add-2008-s (14
+        // unrolled products, ~80 KB each) do not fit the instruction cache and the loop then streams its code from
+        // L2 (ncu: `no_instruction` was the second-largest stall).  The operands rotate through three register sets
+        // U += V with W as the bystander:  A (run += S): U = run, V = S, W = acc;  B (acc += run): U = acc, V = run.
+        XYZZ<F> U = XYZZ<F>::identity(), V = XYZZ<F>::identity(), Wt = XYZZ<F>::identity();
+        bool didA = false;
+        for (uint32_t step = 0; step < 2 * g; step++) {
+            if ((step & 1u) == 0) {
+                const uint32_t k = w * B + (lo + g - 1 - (step >> 1));
+                if (!cnt[k]) continue;          // empty bucket: no A step, layout stays U = acc, V = run
+                Wt = U;                         // acc steps aside
+                U = V;                          // run becomes the destination
+                V = ld_xyzz(items + off[k]);
+                didA = true;
+            } else if (didA) {
+                V = U;                          // run (updated) becomes the source
+                U = Wt;                         // acc the destination
+                didA = false;
+            }
+            xyzz_add(U, V);
         }
-        add_sel(acc, run);
+        acc = U;
+        run = V;
+    } else {
+        run = XYZZ<F>::identity();
+        acc = XYZZ<F>::identity();
+        for (uint32_t b = lo + g; b-- > lo;) {
+            const uint32_t k = w * B + b;
+            if (cnt[k]) {
+                XYZZ<F> S = ld_xyzz(items + off[k]);
+                xyzz_add_ni(run, S);
+            }
+            xyzz_add_ni(acc, run);
+        }
     }
     if (lo != 0 && !run.is_identity()) {
         XYZZ<F> r = XYZZ<F>::identity();
@@ -426,15 +454,22 @@ struct OpsImpl {
         return (unsigned)(need < cap ? (need ? need : 1) : cap);
     }
     static void pair_fwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                         const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T) {
+                         const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, int pf,
+                         const void* xarr) {
         static int occ0 = 0, occ1 = 0;
         if (level0) {
             unsigned grid = pair_grid(k_pair_fwd<F, true>, 256, sm_count, nT_bound, &occ0);
-            ZKM_LAUNCH((k_pair_fwd<F, true>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T);
+            ZKM_LAUNCH((k_pair_fwd<F, true>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T, pf, (const char*)xarr);
         } else {
             unsigned grid = pair_grid(k_pair_fwd<F, false>, 256, sm_count, nT_bound, &occ1);
-            ZKM_LAUNCH((k_pair_fwd<F, false>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T);
+            ZKM_LAUNCH((k_pair_fwd<F, false>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T, pf, (const char*)xarr);
         }
+    }
+    // x coordinates of `n` bases in 64-byte slots (level-0 forward gathers); a no-op for fields without such a layout
+    static void build_xarr(unsigned sm_count, cudaStream_t s, const void* bases, uint64_t n, void* xarr) {
+        if (XArr<F>::SLOT == 0 || n == 0) return;
+        uint64_t blocks = (n + 255) / 256, cap = (uint64_t)sm_count * 8;
+        ZKM_LAUNCH(k_build_xarr<F>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, (const char*)bases, n, (char*)xarr);
     }
     static void pair_inv(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
                          uint32_t m2, void* T, void* pre2) {
@@ -444,14 +479,14 @@ struct OpsImpl {
     }
     static void pair_bwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
                          const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre,
-                         const void* Tinv, void* dst) {
+                         const void* Tinv, void* dst, int pf) {
         static int occ0 = 0, occ1 = 0;
         if (level0) {
             unsigned grid = pair_grid(k_pair_bwd<F, true>, 128, sm_count, nT_bound, &occ0);
-            ZKM_LAUNCH((k_pair_bwd<F, true>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst);
+            ZKM_LAUNCH((k_pair_bwd<F, true>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst, pf);
         } else {
             unsigned grid = pair_grid(k_pair_bwd<F, false>, 128, sm_count, nT_bound, &occ1);
-            ZKM_LAUNCH((k_pair_bwd<F, false>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst);
+            ZKM_LAUNCH((k_pair_bwd<F, false>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst, pf);
         }
     }
     static void reduce(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl,
@@ -518,6 +553,8 @@ struct OpsImpl {
         o.gen_progression = gen_progression;
         o.precompute = precompute;
         o.pair_fwd = pair_fwd;
+        o.build_xarr = build_xarr;
+        o.xarr_slot = XArr<F>::SLOT;
         o.pair_inv = pair_inv;
         o.pair_bwd = pair_bwd;
         o.coord_bytes = CoordIO<F>::BYTES;
