@@ -56,6 +56,7 @@ def lib():
         L.orc_field_op.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, u64p]
         L.orc_msm_window_bits.argtypes = [ctypes.c_size_t]
         L.orc_witness_map.argtypes = [ctypes.c_int, u64p, u64p, u64p, ctypes.c_int, u64p, ctypes.c_int]
+        L.orc_fr_into_repr.argtypes = [ctypes.c_int, u64p, u64p, ctypes.c_size_t]
         _lib = L
     return _lib
 
@@ -166,6 +167,16 @@ def field_op(field: int, op: int, a: np.ndarray, b: np.ndarray = None) -> np.nda
     rc = lib().orc_field_op(field, op, _p64(a), _p64(b), _p64(out))
     if rc:
         raise RuntimeError("orc_field_op rc=%d" % rc)
+    return out
+
+
+def fr_into_repr(curve_id: int, a: np.ndarray) -> np.ndarray:
+    """Fr::into_repr() of every element (Montgomery -> canonical), shape preserved."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, fr_words(curve_id))
+    out = np.zeros_like(a)
+    rc = lib().orc_fr_into_repr(curve_id, _p64(a), _p64(out), len(a))
+    if rc:
+        raise RuntimeError("orc_fr_into_repr rc=%d" % rc)
     return out
 
 

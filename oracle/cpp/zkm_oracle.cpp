@@ -683,6 +683,24 @@ int orc_field_op(int field, int op, const u64* a, const u64* b, u64* out) {
     }
     return -1;
 }
+// Fr::into_repr() over an array (curve ids as above): what KZG10::commit applies to the coefficients
+// (skip_leading_zeros_and_convert_to_bigints, ark-poly-commit 0.3.0 src/kzg10/mod.rs) before the MSM.
+int orc_fr_into_repr(int curve, const u64* in, u64* out, size_t n) {
+#define ORC_REPR(T)                                                  \
+    {                                                                \
+        _Pragma("omp parallel for schedule(static)")                 \
+        for (size_t i = 0; i < n; i++) {                             \
+            Fp<T> x;                                                 \
+            load_fp(x, in + i * T::N);                               \
+            x.into_repr(out + i * T::N);                             \
+        }                                                            \
+        return 0;                                                    \
+    }
+    if (curve == 0) ORC_REPR(BlsFrTag)
+    if (curve == 1) ORC_REPR(BnFrTag)
+    if (curve == 2) ORC_REPR(BwFrTag)
+    return -1;
+}
 // ark-groth16 0.3.0 src/r1cs_to_qap.rs R1CStoQAP::witness_map, the part after a, b, c have been
 // evaluated: ifft(a), ifft(b), coset_fft(a), coset_fft(b), ab = a.b, ifft(c), coset_fft(c), ab -= c,
 // ab *= 1 / Z_H(g) with Z_H(g) = g^n - 1, coset_ifft(ab); returns ab (n coefficients) in h.

@@ -1,0 +1,7 @@
+#!/bin/bash
+# GPU session r1m: Marlin-shaped proxy (BLS12-381 and BW6-761), with CPU restatement and parity of every commitment.
+mkdir -p gpurun_out
+timeout 900 python tools/marlin_proxy.py --log-h 16 --log-k 18 --proofs 6 --cpu > gpurun_out/marlin_proxy_bls12_381_r1.json 2> gpurun_out/marlin.err
+echo "rc=$?"; cat gpurun_out/marlin_proxy_bls12_381_r1.json; tail -3 gpurun_out/marlin.err
+timeout 900 python tools/marlin_proxy.py --curve bw6_761 --log-h 16 --log-k 18 --proofs 4 --cpu > gpurun_out/marlin_proxy_bw6_761_r1.json 2>> gpurun_out/marlin.err
+echo "rc=$?"; cat gpurun_out/marlin_proxy_bw6_761_r1.json; tail -3 gpurun_out/marlin.err
