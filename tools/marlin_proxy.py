@@ -19,7 +19,7 @@ built once in the bench), the commits of a round issued concurrently from host t
 synthesis, the sumcheck polynomial arithmetic and Fiat-Shamir hashing are host Rust and not included, and the
 transform list approximates the AHP's volume (shape, not a transcript).  Prints one JSON line.
 
-  python tools/marlin_proxy.py [--log-h 16] [--log-k 18] [--proofs 6] [--curve bls12_381|bw6_761] [--cpu]
+  python tools/marlin_proxy.py [--log-h 16] [--log-k 18] [--proofs 6] [--curve bls12_381|bw6_761] [--precompute] [--cpu]
 """
 import argparse
 import ctypes
@@ -44,6 +44,7 @@ ap.add_argument("--log-h", type=int, default=16)
 ap.add_argument("--log-k", type=int, default=18)
 ap.add_argument("--proofs", type=int, default=6)
 ap.add_argument("--curve", default="bls12_381")
+ap.add_argument("--precompute", action="store_true", help="register the SRS with precomputed window multiples (static committer key)")
 ap.add_argument("--cpu", action="store_true", help="check every commitment against / time the CPU restatement (1 proof)")
 ap.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")))
 args = ap.parse_args()
@@ -75,7 +76,10 @@ t0 = time.perf_counter()
 d_srs = torch.empty((n_srs, 2 * W1), dtype=torch.int64, device=dev)
 _lib.check(L.zkm_testgen_progression_device(cid, 1, 0x51D5, 0x7, n_srs, ctypes.c_void_p(d_srs.data_ptr()), sp))
 torch.cuda.synchronize()
+if args.precompute:
+    zkm.set_option("msm_precompute", 1)
 powers = zkm.RegisteredBases.from_device(cid, 1, d_srs.data_ptr(), n_srs)
+zkm.set_option("msm_precompute", 0)
 reg_s = time.perf_counter() - t0
 
 # ---- polynomials (host, Montgomery Fr) and transform buffers (device)
@@ -118,7 +122,7 @@ out = {"op": "marlin_proxy", "curve": args.curve, "log_h": args.log_h, "log_k": 
        "ms_per_proof": wall * 1e3, "proofs_per_s": 1.0 / wall, "commits_per_proof": sum(len(r["commits"]) for r in ROUNDS),
        "msm_points_per_proof": int(msm_points), "largest_msm": int(max(m for r in ROUNDS for (_, m) in r["commits"])),
        "ntts_per_proof": sum(len(r["ntts"]) for r in ROUNDS), "ntt_elements_per_proof": int(ntt_elems),
-       "kernel_launches_per_proof": int(launches), "srs_points": int(n_srs), "srs_register_s": reg_s,
+       "precompute": bool(args.precompute), "kernel_launches_per_proof": int(launches), "srs_points": int(n_srs), "srs_register_s": reg_s,
        "h2d_bytes_per_proof": int(msm_points * 8 * SW), "d2h_bytes_per_proof": int(11 * (2 * W1 * 8 + 1)),
        "note": "KZG10 commits (non-hiding part) + radix-2 transforms of Marlin::prove; no synthesis / sumcheck arithmetic / "
                "Fiat-Shamir; transform list approximates the AHP's volume"}

@@ -365,11 +365,23 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     {
         int n_aff = c->opt.msm_affine_levels;
         if (n_aff < 0) {
+            // Measured on B200 (profiles/experiment_affine_threshold_r1p.jsonl, BLS12-381 G1): a pairwise level costs
+            // ~0.33 ns per pair plus ~1 ms of fixed latency (inversion kernel, scans), the XYZZ accumulation it saves
+            // ~0.42 ns per entry -- so a level pays while it still has more than ~6 M pairs, and the whole scheme from
+            // ~24 M entries on (2^21 points: 18.9 -> 16.6 ms with two levels; 2^20: no gain).  Cheaper field products
+            // (BN254: 136 wide MADs instead of 300) raise both thresholds in proportion; they are NOT lowered for the
+            // heavier fields (G2, BW6-761), whose pair kernels run at 2 CTAs/SM and showed no gain below ~24 M entries
+            // (profiles/experiment_affine_rule_r1r.jsonl).
+            const double limbs = (double)ops->coord_bytes / 4.0 / (group == 2 && curve != ZKM_CURVE_BW6_761 ? 2.0 : 1.0);
+            const double mads = (2.0 * limbs * limbs + limbs) * (group == 2 && curve != ZKM_CURVE_BW6_761 ? 3.0 : 1.0);
+            const double scale = mads < 300.0 ? 300.0 / mads : 1.0;   // 1 for BLS12-381 G1
             n_aff = 0;
-            if (entries >= (48u << 20)) {   // avg list length 2^a -> a - 1 levels leave ~2 entries per list
-                double avg = (double)entries / (double)K;
-                while (n_aff < 6 && avg >= 4.0) {
+            if ((double)entries >= 24.0e6 * scale) {
+                double avg = (double)entries / (double)K;   // a level needs lists of >= 4 entries on average
+                double pairs = (double)entries * 0.5;
+                while (n_aff < 8 && avg >= 4.0 && pairs > 6.0e6 * scale) {
                     avg *= 0.5;
+                    pairs *= 0.5;
                     n_aff++;
                 }
             }
