@@ -454,6 +454,24 @@ def main():
         proxy["proofs_per_s_all_gpus"] = float(rates[0])
         proxy["replicas"] = world
 
+    # ---- the other bench configurations of BASELINE.json, rank 0 at N = 1 only (sub-objects, not the headline):
+    # the Marlin-shaped proxy (config 4: KZG10 commits + transforms of one Marlin::prove) and the Groth16 proxy on
+    # BW6-761, the second curve benches/groth16.rs instantiates.
+    extra = {}
+    if rank == 0 and world == 1 and not args.skip_proxy:
+        def run_tool(name, cmd):
+            try:
+                outp = subprocess.run([sys.executable, os.path.join(ROOT, "tools", cmd[0])] + cmd[1:], capture_output=True,
+                                      text=True, timeout=600)
+                extra[name] = json.loads(outp.stdout.strip().splitlines()[-1])
+            except Exception as e:  # noqa: BLE001
+                extra[name] = {"error": repr(e)}
+        torch.cuda.synchronize()
+        run_tool("marlin_proxy", ["marlin_proxy.py", "--log-h", "16", "--log-k", "18", "--proofs", "6"]
+                 + ([] if args.skip_cpu else ["--cpu"]))
+        run_tool("groth16_proxy_bw6_761", ["groth16_proxy.py", "--curve", "bw6_761", "--log-n", "16", "--proofs", "45",
+                                           "--inflight", "3"])
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_baseline_run(1, 0, CPU_SAMPLE_LOG_N)
@@ -473,6 +491,7 @@ def main():
             "msm_stage_ms": {"sort": acc[0], "affine_levels": acc[1], "tasks": acc[2], "accumulate_xyzz": acc[3], "fold": acc[4], "reduce": acc[5]},
             "cpu_baseline": cpu, "ntt": ntt, "groth16_proxy": proxy, "msm_precomputed_bases": pre,
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,8 @@
 //   K5  k_bucket_reduce   running-sum reduction of each window in parallel slices, k_window_sum,
 //       k_msm_final       Horner combine over windows (c doublings each) and normalisation to affine
 // The integer pipe (Montgomery products) bounds K4; everything else is a few percent.  See DESIGN.md.
+#include <math.h>
+
 #include <cub/device/device_scan.cuh>
 
 #include "zkm_msm.cuh"
@@ -177,17 +179,47 @@ __global__ void k_tasks_order(const uint32_t* __restrict__ tlen, const uint32_t*
 static int windows_for(int scalar_bits, int c) { return (scalar_bits + 1 + c - 1) / c; }
 
 // precomputed != 0: the windows share one bucket set (bases registered with window multiples)
-static int auto_window_bits(int curve, size_t n, int precomputed) {
+//
+// Cost model in units of one field product, fitted to sweeps on B200 (profiles/experiment_window_*.jsonl):
+//   * per (point, window): 11 products while the XYZZ accumulation does the work (the 10 of a mixed addition plus the
+//     share of sort and folds), 9.3 falling to 8.3 once the batched-affine levels take over (>= 24 M entries);
+//   * per bucket: 40 (running-sum reduction, ~1.7 ns at BLS12-381 G1) plus a latency term that grows with log2 of the
+//     bucket count -- a reduction over 0.5 M buckets takes 3.8 ms where the throughput term alone says 1 ms;
+//   * SKEW of the top window: it only holds top = bits - c (W - 1) real scalar bits, so its n entries pile into 2^top
+//     buckets: serialised atomics in the histogram / scatter kernels, long lists, extra fold levels.  Measured at
+//     2^23: c = 17 (top 0), 18 (top 3), 19 (top 8) are 7-9 ms slower than the model without this term, c = 16 and 20
+//     (top 15) are not -- which is why c = 16 wins from 2^19 to 2^23 although it has the most windows.
+static int auto_window_bits(int curve, int group, size_t n, int precomputed) {
     const int bits = fr_bits(curve);
     if (n < 2) n = 2;
+    const double limbs = coord_words(curve, 1) * 2.0;
+    const double mads = (2.0 * limbs * limbs + limbs) * ((group == 2 && curve != ZKM_CURVE_BW6_761) ? 3.0 : 1.0);
     double best = 1e300;
     int best_c = 4;
     for (int c = 4; c <= (precomputed ? 24 : 21); c++) {
         double W = windows_for(bits, c);
         double B = (double)(1u << (c - 1));
-        // madd = 10 products per (point, window); per bucket: ~3 full adds (14 products) for the
-        // running-sum reduction and the partial-sum fold, plus sort/bookkeeping
-        double cost = precomputed ? W * (double)n * 10.0 + B * 50.0 : W * ((double)n * 10.0 + B * 50.0);
+        double cost;
+        if (precomputed) {
+            cost = W * (double)n * 10.0 + B * 50.0;
+        } else {
+            const double K = W * B;
+            int top = bits - c * ((int)W - 1);
+            if (top < 0) top = 0;
+            if (top > c - 1) top = c - 1;
+            const double E = W * (double)n;
+            double per_entry = 11.0;
+            if (E >= 24.0e6) {
+                double lgE = log2(E / 24.0e6) * 0.5;
+                per_entry = 9.3 - (lgE < 1.0 ? lgE : 1.0);
+            }
+            cost = E * per_entry + K * 40.0;
+            if (K > 32768.0) {
+                double lg = log2(K / 32768.0);
+                cost += 9.0e6 * (lg < 6.0 ? lg : 6.0);
+            }
+            cost += 30.0 * (double)n * (1.0 - (double)top / (double)(c - 1));
+        }
         if (cost < best) {
             best = cost;
             best_c = c;
@@ -207,8 +239,7 @@ static int auto_window_bits(int curve, size_t n, int precomputed) {
 }
 
 int msm_auto_window_bits(int curve, int group, size_t n) {
-    (void)group;
-    return auto_window_bits(curve, n, 0);
+    return auto_window_bits(curve, group, n, 0);
 }
 
 static const CurveOps* curve_ops(int curve, int group) {
@@ -239,7 +270,7 @@ static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t
 void msm_precompute(Context* c, BasesReg* reg, cudaStream_t s) {
     const CurveOps* ops = curve_ops(reg->curve, reg->group);
     if (reg->n == 0) return;
-    int cb = c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : auto_window_bits(reg->curve, reg->n, 1);
+    int cb = c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : auto_window_bits(reg->curve, reg->group, reg->n, 1);
     if (cb < 2) cb = 2;
     if (cb > 24) cb = 24;
     int W = windows_for(ops->scalar_bits, cb);
