@@ -499,4 +499,25 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on stdout) and anything
+    # else written to fd 1 during the run go to stderr instead; the line itself is written to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    _buf = io.StringIO()
+    _orig = sys.stdout
+    sys.stdout = _buf
+    try:
+        _rc = main()
+    finally:
+        sys.stdout = _orig
+        _lines = [l for l in _buf.getvalue().splitlines() if l.strip()]
+        _json = [l for l in _lines if l.lstrip().startswith("{")]
+        for l in _lines:
+            if l not in _json[-1:]:
+                sys.stderr.write(l + "\n")
+        if _json:
+            os.write(_real_stdout, (_json[-1] + "\n").encode())
+        os.close(_real_stdout)
+    sys.exit(_rc)
