@@ -457,19 +457,31 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, cur_cnt, K, L1, tpb[0], flags);
     exclusive_scan(c, tpb[0], tbase[0], K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(h_flags, flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    // the one host sync: largest bucket -> depth of the fold tree.  A spinning wait is the fastest when few
-    // calls are in flight; with many concurrent lanes (batched proofs) the spinning host threads starve each
-    // other, so they block on an event instead.
+    // The one host read-back: largest bucket -> depth of the fold tree.  Only the fold loop needs it, so the event is
+    // recorded right after the copy and waited for AFTER the level-1 task list and the bucket accumulation have been
+    // enqueued: the GPU keeps working through the host round trip instead of idling behind it.  A spinning wait is
+    // the fastest when few calls are in flight; with many concurrent lanes (batched proofs) the spinning host threads
+    // starve each other, so they block on an event instead.
+    static cudaEvent_t spin_ev[ZKM_NUM_LANES] = {};   // per lane (a lane has one borrower at a time)
+    static int spin_dev[ZKM_NUM_LANES] = {};
+    cudaEvent_t fev;
     if (busy_lane_count() > 6) {
         if (!c->sync_ev) ZKM_CUDA(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
-        ZKM_CUDA(cudaEventRecord(c->sync_ev, s));
-        ZKM_CUDA(cudaEventSynchronize(c->sync_ev));
+        fev = c->sync_ev;
     } else {
-        ZKM_CUDA(cudaStreamSynchronize(s));
+        const int li = c->lane_id % ZKM_NUM_LANES;
+        cudaEvent_t& e = spin_ev[li];
+        if (e && spin_dev[li] != c->device) {       // re-initialised on another device
+            cudaEventDestroy(e);
+            e = nullptr;
+        }
+        if (!e) {
+            ZKM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            spin_dev[li] = c->device;
+        }
+        fev = e;
     }
-    if (h_flags[1])
-        ZKM_FAIL(ZKM_ERR_SCALAR_RANGE, "a scalar has bits at or above bit %d (not a canonical Fr)", pl.scalar_bits + 1);
-    const uint32_t maxcnt = h_flags[0];
+    ZKM_CUDA(cudaEventRecord(fev, s));
 
     auto build_tasks = [&](const uint32_t* tb, const uint32_t* offs, const uint32_t* cnts, uint32_t L) {
         ZKM_CUDA(cudaMemsetAsync(lenhist, 0, (L + 1) * sizeof(uint32_t), s));
@@ -485,6 +497,10 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     ops->accum_affine(grid_acc, s, cur_src, cur_idx, TaskList{tstart, tlen, order, tbase[0], K}, part[0]);
 
     mark(4);
+    ZKM_CUDA(cudaEventSynchronize(fev));
+    if (h_flags[1])
+        ZKM_FAIL(ZKM_ERR_SCALAR_RANGE, "a scalar has bits at or above bit %d (not a canonical Fr)", pl.scalar_bits + 1);
+    const uint32_t maxcnt = h_flags[0];
     int cur = 0;  // tpb[cur] / tbase[cur] / part[cur] describe the current partial sums
     uint32_t maxseg = (maxcnt + L1 - 1) / L1;
     while (maxseg > 1) {
