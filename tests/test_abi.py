@@ -86,3 +86,20 @@ def test_window_bits_heuristic_is_monotone():
         c = msm_window_bits("bls12_381", 1, 1 << k)
         assert 2 <= c <= 24 and c >= prev
         prev = c
+
+
+def test_window_model_matches_measured_optima():
+    """The automatic window size is a cost model fitted to B200 sweeps; these are the measured
+    optima it must keep reproducing: full top windows (c = 16, 20 for 255-bit scalars) once the sort matters."""
+    from zkmember_b200 import msm_window_bits
+    assert [msm_window_bits("bls12_381", 1, 1 << k) for k in (20, 21, 22, 23)] == [16, 16, 16, 16]
+    assert [msm_window_bits("bls12_381", 1, 1 << k) for k in (24, 25, 26)] == [20, 20, 20]
+    assert msm_window_bits("bls12_381", 1, 1 << 17) in (11, 12)
+    assert msm_window_bits("bn254", 1, 1 << 22) == 17            # 254 = 14 * 17 + 16: a full top window
+    assert msm_window_bits("bw6_761", 1, 1 << 20) == 14          # 377 = 26 * 14 + 13
+    for curve in ("bls12_381", "bn254", "bw6_761"):
+        prev = 0
+        for k in range(4, 27):
+            c = msm_window_bits(curve, 1, 1 << k)
+            assert 2 <= c <= 24 and c >= prev, (curve, k, c)
+            prev = c
