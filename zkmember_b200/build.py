@@ -19,17 +19,18 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libzkm_b200.so")
 
-UNITS = [
+UNITS = [   # the slowest units first: with fewer cores than units they must start right away
+    "zkm_msm_bw6.cu",
+    "zkm_msm_g2_bls.cu",
+    "zkm_msm_bw6_pair.cu",
     "zkm_api.cu",
     "zkm_ntt_bls.cu",
     "zkm_ntt_bn.cu",
     "zkm_msm.cu",
     "zkm_msm_g1_bls.cu",
-    "zkm_msm_g2_bls.cu",
     "zkm_msm_g1_bn.cu",
     "zkm_msm_g2_bn.cu",
     "zkm_ntt_bw6.cu",
-    "zkm_msm_bw6.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -56,6 +57,7 @@ UNIT_HEADERS = {
     "zkm_msm_g2_bn.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
     "zkm_ntt_bw6.cu": ["zkm_ntt.cuh"],
     "zkm_msm_bw6.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
+    "zkm_msm_bw6_pair.cu": ["zkm_msm.cuh", "zkm_msm_curve.cuh", "zkm_msm_affine.cuh", "zkm_msm_quad.cuh"],
 }
 
 

@@ -432,6 +432,22 @@ __global__ void __launch_bounds__(128) k_precompute(const char* __restrict__ bas
 }
 
 // ---------------------------------------------------------------------------------- ops table
+// Build-time split: for the 761-bit field the batched-affine pair kernels are compiled in their own translation unit
+// (zkm_msm_bw6_pair.cu) so that ptxas works on the two halves of the group in parallel.  `external` = true makes
+// OpsImpl<G>::make() take the pair launchers from there instead of instantiating them in the including unit.
+template <class G> struct PairOpsProvider { static constexpr bool external = false; };
+template <> struct PairOpsProvider<G1Bw6> { static constexpr bool external = true; };
+template <> struct PairOpsProvider<G2Bw6> { static constexpr bool external = true; };
+void bw6_pair_fwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
+                  const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, int pf,
+                  const void* xarr);
+void bw6_pair_inv(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
+                  uint32_t m2, void* T, void* pre2);
+void bw6_pair_bwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
+                  const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
+                  void* dst, int pf);
+void bw6_build_xarr(unsigned sm_count, cudaStream_t s, const void* bases, uint64_t n, void* xarr);
+
 template <class G>
 struct OpsImpl {
     typedef typename G::F F;
@@ -552,11 +568,18 @@ struct OpsImpl {
         o.points_sum = points_sum;
         o.gen_progression = gen_progression;
         o.precompute = precompute;
-        o.pair_fwd = pair_fwd;
-        o.build_xarr = build_xarr;
+        if constexpr (PairOpsProvider<G>::external) {
+            o.pair_fwd = bw6_pair_fwd;
+            o.build_xarr = bw6_build_xarr;
+            o.pair_inv = bw6_pair_inv;
+            o.pair_bwd = bw6_pair_bwd;
+        } else {
+            o.pair_fwd = pair_fwd;
+            o.build_xarr = build_xarr;
+            o.pair_inv = pair_inv;
+            o.pair_bwd = pair_bwd;
+        }
         o.xarr_slot = XArr<F>::SLOT;
-        o.pair_inv = pair_inv;
-        o.pair_bwd = pair_bwd;
         o.coord_bytes = CoordIO<F>::BYTES;
         return o;
     }
