@@ -34,21 +34,22 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, q):
+def _worker(rank, world, port, n, q, curve_name="bls12_381"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import capi
     from oracle.py import exact
-    from oracle.py.params import BLS12_381
+    from oracle.py.params import CURVES
     from zkmember_b200.dist import sharded_msm
-    curve = BLS12_381
-    bases = capi.progression(0, 1, 17, 3, n)
-    scal = capi.random_scalars(0, n, seed=99)
-    W = 6
+    curve = CURVES[curve_name]
+    cid = curve.curve_id
+    bases = capi.progression(cid, 1, 17, 3, n)
+    scal = capi.random_scalars(cid, n, seed=99)
+    W = curve.fq.limbs64
 
     def local_msm(lo, hi):      # stands in for RegisteredBases.msm_device on this rank's GPU
-        xy, inf = capi.msm(0, 1, bases[lo:hi], scal[lo:hi])
+        xy, inf = capi.msm(cid, 1, bases[lo:hi], scal[lo:hi])
         rec = np.concatenate([xy, np.array([1 if inf else 0], dtype=np.uint64)])
         return torch.from_numpy(rec.view(np.int64).copy())
 
@@ -61,18 +62,18 @@ def _worker(rank, world, port, n, q):
         return b, f
 
     got = sharded_msm(n, rank, world, local_msm, sum_records)
-    want_xy, want_inf = capi.msm(0, 1, bases, scal)
+    want_xy, want_inf = capi.msm(cid, 1, bases, scal)
     q.put((rank, got[0] == want_xy.tobytes() and bool(got[1]) == want_inf))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [1, 1001])
-def test_sharded_msm_world2_gloo(n):
-    assert record_words(6) == 13
+@pytest.mark.parametrize("n,curve_name", [(1, "bls12_381"), (1001, "bls12_381"), (301, "bw6_761")])
+def test_sharded_msm_world2_gloo(n, curve_name):
+    assert record_words(6) == 13 and record_words(12) == 25      # BLS12-381 / BW6-761 G1 result records
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q, curve_name)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in procs)
