@@ -9,6 +9,7 @@
 //                                                               ark-poly 0.3.0 src/domain/radix2/mod.rs
 //   zkm::witness_map(domain, a, b, c)                           ark-groth16 0.3.0 src/r1cs_to_qap.rs
 //   zkm::ProvingKeyBases / KZG10::commit                        registered bases (pk / SRS reuse)
+//   zkm::serialize(point) / zkm::Proof<Curve>::serialize()      arkworks' compressed CanonicalSerialize (host code)
 //
 // Types are plain structs with arkworks' memory layout: Fp256 = 4 x u64 Montgomery limbs, Fp384 = 6,
 // BigInteger256 = 4 x u64 canonical limbs (BigInteger384 = 6 for BW6-761), GroupAffine{x, y, infinity}.  Errors of the C ABI become
@@ -59,6 +60,11 @@ struct Bls12_381 {
     typedef Fp<6> Fq;
     typedef Fp2<6> G2Coord;
     typedef BigInteger256 BigInt;
+    static constexpr int FQ_BITS = 381;
+    static const uint64_t* fq_modulus() {
+        static const uint64_t m[6] = {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL, 0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL};
+        return m;
+    }
 };
 struct Bn254 {
     static constexpr int ID = ZKM_CURVE_BN254;
@@ -67,6 +73,11 @@ struct Bn254 {
     typedef Fp<4> Fq;
     typedef Fp2<4> G2Coord;
     typedef BigInteger256 BigInt;
+    static constexpr int FQ_BITS = 254;
+    static const uint64_t* fq_modulus() {
+        static const uint64_t m[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+        return m;
+    }
 };
 // The second curve zkMember instantiates (/root/reference/benches/groth16.rs:24-29): 761-bit Fq, 377-bit Fr
 // (= the base field of BLS12-377), and a G2 that is a curve over Fq itself.
@@ -77,6 +88,11 @@ struct Bw6_761 {
     typedef Fp<12> Fq;
     typedef Fp<12> G2Coord;
     typedef BigInteger384 BigInt;
+    static constexpr int FQ_BITS = 761;
+    static const uint64_t* fq_modulus() {
+        static const uint64_t m[12] = {0xf49d00000000008bULL, 0xe6913e6870000082ULL, 0x160cf8aeeaf0a437ULL, 0x98a116c25667a8f8ULL, 0x71dcd3dc73ebff2eULL, 0x8689c8ed12f9fd90ULL, 0x03cebaff25b42304ULL, 0x707ba638e584e919ULL, 0x528275ef8087be41ULL, 0xb926186a81d14688ULL, 0xd187c94004faff3eULL, 0x0122e824fb83ce0aULL};
+        return m;
+    }
 };
 
 // GroupAffine<P>: x, y, infinity.  G1: Coord = Fq; G2: Coord = Fp2<Fq limbs> (BW6-761: Fq).
@@ -237,6 +253,124 @@ struct KZG10 {
         check(zkm_kzg_commit(powers_of_g.handle(), reinterpret_cast<const uint64_t*>(coeffs.data()), coeffs.size(), out.data(), &out_inf),
               "zkm_kzg_commit");
         return detail::unpack<Curve, 1>(out, out_inf);
+    }
+};
+
+// ---- arkworks CanonicalSerialize (compressed) for affine points and Groth16 proofs -------------------------------
+// ark-ec 0.3.0 GroupAffine::serialize (src/models/short_weierstrass_jacobian.rs) + ark-ff 0.3.0
+// Fp::serialize_with_flags / QuadExtField::serialize_with_flags + ark-serialize 0.3.0 SWFlags: x canonical
+// little-endian in ceil((MODULUS_BITS + 2) / 8) bytes, bit 7 of the last byte = "y > -y", bit 6 = infinity; an Fp2
+// writes c0 without flags and c1 with them and is ordered by c1 first.  The wire format of zkMember's proofs
+// (/root/reference/src/main.rs:164-169).  Host-side glue on a handful of elements -- plain C++, no GPU involved.
+namespace detail {
+// out = a * R^-1 mod p (Montgomery reduction of a single element: into_repr), L limbs
+template <int L>
+inline void from_mont(const uint64_t* a, const uint64_t* p, uint64_t* out) {
+    uint64_t inv = 1;                                   // p^-1 mod 2^64 by Newton, then negated
+    for (int i = 0; i < 6; i++) inv *= 2 - p[0] * inv;
+    inv = 0 - inv;
+    uint64_t t[L + 1];
+    for (int i = 0; i < L; i++) t[i] = a[i];
+    t[L] = 0;
+    for (int i = 0; i < L; i++) {
+        const uint64_t m = t[0] * inv;
+        unsigned __int128 carry = ((unsigned __int128)m * p[0] + t[0]) >> 64;
+        for (int j = 1; j < L; j++) {
+            unsigned __int128 v = (unsigned __int128)m * p[j] + t[j] + (uint64_t)carry;
+            t[j - 1] = (uint64_t)v;
+            carry = v >> 64;
+        }
+        unsigned __int128 v = (unsigned __int128)t[L] + (uint64_t)carry;
+        t[L - 1] = (uint64_t)v;
+        t[L] = (uint64_t)(v >> 64);
+    }
+    bool ge = t[L] != 0;                                // t < 2p: one conditional subtraction
+    if (!ge) {
+        ge = true;
+        for (int i = L - 1; i >= 0; i--) {
+            if (t[i] != p[i]) { ge = t[i] > p[i]; break; }
+        }
+    }
+    uint64_t borrow = 0;
+    for (int i = 0; i < L; i++) {
+        if (ge) {
+            unsigned __int128 d = (unsigned __int128)t[i] - p[i] - borrow;
+            out[i] = (uint64_t)d;
+            borrow = (uint64_t)(d >> 64) & 1;
+        } else {
+            out[i] = t[i];
+        }
+    }
+}
+template <int L>
+inline void neg_canonical(const uint64_t* a, const uint64_t* p, uint64_t* out) {     // (p - a) mod p
+    bool zero = true;
+    for (int i = 0; i < L; i++) zero = zero && a[i] == 0;
+    uint64_t borrow = 0;
+    for (int i = 0; i < L; i++) {
+        unsigned __int128 d = (unsigned __int128)p[i] - a[i] - borrow;
+        out[i] = zero ? 0 : (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+}
+template <int L>
+inline int cmp_limbs(const uint64_t* a, const uint64_t* b) {
+    for (int i = L - 1; i >= 0; i--)
+        if (a[i] != b[i]) return a[i] > b[i] ? 1 : -1;
+    return 0;
+}
+inline void put_le(std::vector<uint8_t>& out, const uint64_t* v, int limbs, size_t bytes) {
+    for (size_t i = 0; i < bytes; i++) out.push_back((size_t)(i / 8) < (size_t)limbs ? (uint8_t)(v[i / 8] >> (8 * (i % 8))) : 0);
+}
+// canonical limbs of the DEG Fq elements of a coordinate (Fp: 1, Fp2: 2)
+template <int L>
+inline void coord_canonical(const Fp<L>& c, const uint64_t* p, uint64_t (*out)[12]) { from_mont<L>(c.limbs, p, out[0]); }
+template <int L>
+inline void coord_canonical(const Fp2<L>& c, const uint64_t* p, uint64_t (*out)[12]) {
+    from_mont<L>(c.c0.limbs, p, out[0]);
+    from_mont<L>(c.c1.limbs, p, out[1]);
+}
+template <int L> constexpr int coord_degree(const Fp<L>*) { return 1; }
+template <int L> constexpr int coord_degree(const Fp2<L>*) { return 2; }
+}  // namespace detail
+
+template <class Curve, int GROUP>
+inline std::vector<uint8_t> serialize(const GroupAffine<Curve, GROUP>& pt) {
+    typedef typename GroupAffine<Curve, GROUP>::Coord Coord;
+    constexpr int L = sizeof(typename Curve::Fq) / 8;
+    constexpr int DEG = detail::coord_degree((const Coord*)nullptr);
+    const uint64_t* p = Curve::fq_modulus();
+    const size_t plain = (Curve::FQ_BITS + 7) / 8, flagged = (Curve::FQ_BITS + 2 + 7) / 8;
+    uint64_t x[2][12] = {}, y[2][12] = {}, ny[2][12] = {};
+    uint8_t flag;
+    if (pt.infinity) {
+        flag = 1u << 6;                                  // SWFlags::Infinity, x = 0
+    } else {
+        detail::coord_canonical(pt.x, p, x);
+        detail::coord_canonical(pt.y, p, y);
+        for (int d = 0; d < DEG; d++) detail::neg_canonical<L>(y[d], p, ny[d]);
+        int c = 0;                                       // y > -y; Fp2: c1 first, then c0
+        for (int d = DEG - 1; d >= 0 && c == 0; d--) c = detail::cmp_limbs<L>(y[d], ny[d]);
+        flag = c > 0 ? (1u << 7) : 0;                    // PositiveY | NegativeY
+    }
+    std::vector<uint8_t> out;
+    for (int d = 0; d + 1 < DEG; d++) detail::put_le(out, x[d], L, plain);
+    detail::put_le(out, x[DEG - 1], L, flagged);
+    out.back() |= flag;
+    return out;
+}
+
+// ark_groth16::Proof { a: G1Affine, b: G2Affine, c: G1Affine }: a || b || c
+template <class Curve>
+struct Proof {
+    G1Affine<Curve> a;
+    G2Affine<Curve> b;
+    G1Affine<Curve> c;
+    std::vector<uint8_t> serialize() const {
+        std::vector<uint8_t> out = zkm::serialize(a), sb = zkm::serialize(b), sc = zkm::serialize(c);
+        out.insert(out.end(), sb.begin(), sb.end());
+        out.insert(out.end(), sc.begin(), sc.end());
+        return out;
     }
 };
 

@@ -3,6 +3,7 @@
 //   ntt <curve> <log_n> <inverse> <coset> <hex input> <hex output>
 //   msm <curve> <group> <n> <hex bases> <hex infinity flags> <hex scalars> <hex result> <result infinity>
 //   wmap <curve> <log_n> <hex a> <hex b> <hex c> <hex h>
+//   ser <curve> <group> <hex xy> <infinity> <hex compressed>     (host-only: checked BEFORE zkm::init, no GPU needed)
 // Byte equality is the bar.  Exit code 0 = all vectors match.
 #include <cstdio>
 #include <fstream>
@@ -69,8 +70,41 @@ static bool run_wmap(int log_n, const std::vector<uint8_t>& a, const std::vector
     return std::memcmp(h.data(), want.data(), n * sizeof(F)) == 0;
 }
 
+template <class Curve, int GROUP>
+static bool run_ser(const std::vector<uint8_t>& xy, int inf, const std::vector<uint8_t>& want) {
+    typedef zkm::GroupAffine<Curve, GROUP> A;
+    typedef typename A::Coord Coord;
+    A pt;
+    std::memcpy(&pt.x, xy.data(), sizeof(Coord));
+    std::memcpy(&pt.y, xy.data() + sizeof(Coord), sizeof(Coord));
+    pt.infinity = inf != 0;
+    return zkm::serialize(pt) == want;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { std::fprintf(stderr, "usage: %s vectors.txt\n", argv[0]); return 2; }
+    {   // arkworks compressed serialization: pure host code, runs with or without a GPU
+        std::ifstream f(argv[1]);
+        std::string line;
+        int total = 0, bad = 0;
+        while (std::getline(f, line)) {
+            std::istringstream is(line);
+            std::string kind, curve, hxy, hwant;
+            int group, inf;
+            is >> kind;
+            if (kind != "ser") continue;
+            is >> curve >> group >> hxy >> inf >> hwant;
+            auto XY = unhex(hxy), W = unhex(hwant);
+            bool ok;
+            if (curve == "bls12_381") ok = group == 1 ? run_ser<zkm::Bls12_381, 1>(XY, inf, W) : run_ser<zkm::Bls12_381, 2>(XY, inf, W);
+            else if (curve == "bn254") ok = group == 1 ? run_ser<zkm::Bn254, 1>(XY, inf, W) : run_ser<zkm::Bn254, 2>(XY, inf, W);
+            else ok = group == 1 ? run_ser<zkm::Bw6_761, 1>(XY, inf, W) : run_ser<zkm::Bw6_761, 2>(XY, inf, W);
+            total++;
+            if (!ok) { bad++; std::printf("MISMATCH: ser %s g%d (vector %d)\n", curve.c_str(), group, total); }
+        }
+        std::printf("ser: %d vectors, %d mismatches\n", total, bad);
+        if (bad) return 1;
+    }
     try {
         zkm::init(0);
     } catch (const zkm::Error& e) {

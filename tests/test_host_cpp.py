@@ -39,8 +39,22 @@ def _vectors(path):
         a, b, c = (capi.random_field_elements(cid, n, seed=s) for s in (21, 22, 23))
         h = capi.witness_map(cid, a, b, c)
         lines.append("wmap %s 9 %s %s %s %s" % (name, a.tobytes().hex(), b.tobytes().hex(), c.tobytes().hex(), h.tobytes().hex()))
+    # arkworks compressed serialization (host-only lines, checked before zkm::init)
+    from oracle.py import exact, groth16_exact as gx
+    from oracle.py.params import CURVES
+    n_ser = 0
+    for name in ("bls12_381", "bn254", "bw6_761"):
+        curve = CURVES[name]
+        for g in (1, 2):
+            G = exact.Group(curve, g)
+            pts = G.progression(7, 5, 8) + [None]
+            pts += [G.neg(P) for P in pts[:4]]
+            for P in pts:
+                b, f = exact.point_to_bytes(curve, g, P)
+                lines.append("ser %s %d %s %d %s" % (name, g, b.hex(), f, gx.serialize_affine(curve, g, P).hex()))
+                n_ser += 1
     open(path, "w").write("\n".join(lines) + "\n")
-    return len(lines)
+    return len(lines) - n_ser, n_ser
 
 
 def test_cpp_host_layer_builds_and_has_no_cpu_fallback(tmp_path):
@@ -49,8 +63,10 @@ def test_cpp_host_layer_builds_and_has_no_cpu_fallback(tmp_path):
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     vec = tmp_path / "v.txt"
-    _vectors(str(vec))
+    _, n_ser = _vectors(str(vec))
     r = subprocess.run([exe, str(vec)], capture_output=True, text=True)
+    # the host-only part (arkworks compressed serialization) runs without a GPU and must match the restatement
+    assert "ser: %d vectors, 0 mismatches" % n_ser in r.stdout, r.stdout[-2000:]
     assert r.returncode == 3 and "INIT FAILED" in r.stdout and "no CPU fallback" in r.stdout
 
 
@@ -58,7 +74,8 @@ def test_cpp_host_layer_builds_and_has_no_cpu_fallback(tmp_path):
 def test_cpp_host_layer_matches_golden_vectors(tmp_path):
     exe = _build()
     vec = tmp_path / "v.txt"
-    count = _vectors(str(vec))
+    count, n_ser = _vectors(str(vec))
     r = subprocess.run([exe, str(vec)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "%d vectors, 0 mismatches" % count in r.stdout
+    assert "ser: %d vectors, 0 mismatches" % n_ser in r.stdout
+    assert "host_cpp: %d vectors, 0 mismatches" % count in r.stdout
