@@ -6,6 +6,7 @@ use std::os::raw::{c_char, c_void};
 
 pub const ZKM_CURVE_BLS12_381: i32 = 0;
 pub const ZKM_CURVE_BN254: i32 = 1;
+pub const ZKM_CURVE_BW6_761: i32 = 2; // 12-word coordinates (G1 and G2 both over Fq), 6-word scalars / Fr elements
 pub const ZKM_OK: i32 = 0;
 pub const ZKM_ERR_DOMAIN: i32 = -4;
 
@@ -24,7 +25,10 @@ extern "C" {
     pub fn zkm_msm_registered(handle: u64, offset: usize, scalars: *const u64, n: usize, out_xy: *mut u64,
                               out_inf: *mut u8) -> i32;
     pub fn zkm_ntt(curve: i32, data: *mut u64, log_n: u32, inverse: i32, coset: i32) -> i32;
-    pub fn zkm_domain_constants(curve: i32, log_n: u32, out5x4: *mut u64) -> i32;
+    pub fn zkm_domain_constants(curve: i32, log_n: u32, out5x_s64: *mut u64) -> i32;
+    pub fn zkm_witness_map(curve: i32, a: *const u64, b: *const u64, c: *const u64, log_n: u32, h_out: *mut u64) -> i32;
+    pub fn zkm_kzg_commit(handle: u64, coeffs: *const u64, n: usize, out_xy: *mut u64, out_inf: *mut u8) -> i32;
+    pub fn zkm_set_option(key: *const c_char, value: i64) -> i32;
     pub fn zkm_ntt_device(curve: i32, d_in: *const u64, d_out: *mut u64, log_n: u32, inverse: i32, coset: i32,
                           stream: *mut c_void) -> i32;
     pub fn zkm_msm_registered_device(handle: u64, offset: usize, d_scalars: *const u64, n: usize, d_out: *mut u64,
