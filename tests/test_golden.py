@@ -32,7 +32,7 @@ def test_golden_files_are_reproducible():
     with tempfile.TemporaryDirectory() as tmp:
         shutil.copytree(os.path.join(root, "tests", "golden"), os.path.join(tmp, "golden"))
         subprocess.check_call(["python", os.path.join(root, "tools", "gen_golden.py")], stdout=subprocess.DEVNULL)
-        for f in ("ntt_vectors.json", "msm_vectors.json"):
+        for f in ("ntt_vectors.json", "msm_vectors.json", "wmap_vectors.json"):
             assert open(os.path.join(tmp, "golden", f)).read() == open(os.path.join(HERE, "golden", f)).read(), f
 
 
@@ -50,6 +50,14 @@ def test_oracle_msm_golden(i):
     xy, inf = capi.msm(CID[v["curve"]], v["group"], _u64(v["bases"], 2 * W), _u64(v["scalars"], SW[v["curve"]]),
                        np.array(v["infinity"], dtype=np.uint8))
     assert int(inf) == v["result_infinity"] and xy.tobytes().hex() == v["result"]
+
+
+def test_oracle_witness_map_golden():
+    """The C++ restatement of witness_map (io/oi helpers, distribute_powers) against the exact-definition fixture."""
+    for v in json.load(open(os.path.join(HERE, "golden", "wmap_vectors.json")))["vectors"]:
+        S = SW[v["curve"]]
+        h = capi.witness_map(CID[v["curve"]], _u64(v["a"], S), _u64(v["b"], S), _u64(v["c"], S))
+        assert h.tobytes().hex() == v["h"], v["curve"]
 
 
 @pytest.mark.gpu

@@ -80,8 +80,24 @@ def msm_vectors():
     return vecs
 
 
+def wmap_vectors():
+    """R1CStoQAP::witness_map (ark-groth16 0.3.0 src/r1cs_to_qap.rs) from the exact O(n^2) definitions, n = 8."""
+    from oracle.py import groth16_exact as gx
+    vecs = []
+    for curve in (BLS12_381, BN254, BW6_761):
+        fr = curve.fr
+        rng = random.Random(3000 + curve.curve_id)
+        a, b, c = ([rng.randrange(fr.modulus) for _ in range(8)] for _ in range(3))
+        h = gx.witness_map(curve, a, b, c)
+        enc = lambda v: hexs(b"".join(exact.fe_to_bytes(fr, x) for x in v))
+        vecs.append({"curve": curve.name, "log_n": 3, "a": enc(a), "b": enc(b), "c": enc(c), "h": enc(h)})
+    return vecs
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    json.dump({"generator": "tools/gen_golden.py", "format": "Montgomery LE limbs, hex", "vectors": wmap_vectors()},
+              open(os.path.join(OUT, "wmap_vectors.json"), "w"), indent=0)
     json.dump({"generator": "tools/gen_golden.py", "format": "Montgomery LE limbs, hex", "vectors": ntt_vectors()},
               open(os.path.join(OUT, "ntt_vectors.json"), "w"), indent=0)
     json.dump({"generator": "tools/gen_golden.py", "format": "affine Montgomery LE limbs / canonical LE scalars, hex",
