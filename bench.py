@@ -508,6 +508,7 @@ if __name__ == "__main__":
     _buf = io.StringIO()
     _orig = sys.stdout
     sys.stdout = _buf
+    _rc = 1
     try:
         _rc = main()
     finally:
