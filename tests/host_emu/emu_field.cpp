@@ -22,6 +22,8 @@ static void fp_ops(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, 
             case 5: r = inv(x); break;
             case 6: r = dbl(x); break;
             case 7: r = fp_inv_fermat(x); break;
+            case 8: r = fp_mul_unsat(x, y); break;   // unsaturated-radix column product (zkm_fpmul_u.cuh)
+            case 9: r = fp_sqr_unsat(x); break;
             default: r = F::zero();
         }
         memcpy(out + k * N, r.l, 4 * N);

@@ -20,7 +20,8 @@ CSRC = os.path.join(os.path.dirname(HERE), "zkmember_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("zkm_arith.cuh", "zkm_field.cuh", "zkm_curve.cuh", "zkm_constants.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("zkm_arith.cuh", "zkm_field.cuh", "zkm_curve.cuh", "zkm_constants.cuh",
+                                                     "zkm_fpmul_u.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-DZKM_HOST_EMU", "-x", "c++", "-shared", "-fPIC", "-o", OUT, SRC])
@@ -48,7 +49,7 @@ def test_fp_ops(emu, fid):
     B = np.array([_limbs32(fp.to_mont(v), n) for v in reversed(vals)], dtype=np.uint32)
     out = np.zeros_like(A)
     ops = {0: lambda a, b: a * b % p, 1: lambda a, b: (a + b) % p, 2: lambda a, b: (a - b) % p, 3: lambda a, b: (-a) % p,
-           4: lambda a, b: a * a % p, 6: lambda a, b: 2 * a % p}
+           4: lambda a, b: a * a % p, 6: lambda a, b: 2 * a % p, 8: lambda a, b: a * b % p}
     for op, f in ops.items():
         assert emu.emu_fp_op(fid, op, _p(A), _p(B), _p(out), len(vals)) == 0
         for i, (a, b) in enumerate(zip(vals, reversed(vals))):
@@ -72,6 +73,44 @@ def test_fp_ops(emu, fid):
     Z = np.zeros((1, n), dtype=np.uint32)
     oz = np.ones_like(Z)
     assert emu.emu_fp_op(fid, 5, _p(Z), _p(Z), _p(oz), 1) == 0 and not oz.any()
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3, 4, 5])
+def test_fp_mul_unsaturated_extreme_limbs(emu, fid):
+    """The carry-free column product (zkm_fpmul_u.cuh) on RAW representatives chosen to maximise the column sums:
+    p - 1, all-ones below the modulus width, every r-bit limb saturated, sparse patterns, and 2000 random pairs;
+    the unsaturated product and squaring and the saturated CIOS (ops 0 / 4) must all equal x * y * R^-1 mod p."""
+    fp = FIELDS[fid]
+    p, n = fp.modulus, fp.limbs32
+    Rinv = pow(1 << (32 * n), -1, p)
+    rng = np.random.default_rng(100 + fid)
+    top = (1 << (p.bit_length() - 1)) - 1
+    raw = [0, 1, p - 1, p - 2, top, top - 1, (1 << (p.bit_length() - 1)), p >> 1, (p - 1) ^ 0x5555555555555555]
+    for r in (29, 30):
+        m = 0
+        for i in range(0, p.bit_length() + r, r):
+            m |= ((1 << r) - 1) << i
+        raw += [m % p, (m >> 1) % p, (m & top)]
+    raw = [v % p for v in raw]
+    raw += [int.from_bytes(rng.bytes(104), "little") % p for _ in range(2000)]
+    A = np.array([_limbs32(v, n) for v in raw], dtype=np.uint32)
+    B = np.array([_limbs32(v, n) for v in raw[::-1]], dtype=np.uint32)
+    for op in (0, 8, 4, 9):
+        out = np.zeros_like(A)
+        assert emu.emu_fp_op(fid, op, _p(A), _p(B), _p(out), len(raw)) == 0
+        for i, (a, b) in enumerate(zip(raw, raw[::-1])):
+            want = (a * (a if op in (4, 9) else b) * Rinv) % p
+            assert sum(int(out[i, j]) << (32 * j) for j in range(n)) == want, (fid, op, i)
+    # every ordered pair of the extreme values
+    ext = raw[:15]
+    pa = [a for a in ext for _ in ext]
+    pb = [b for _ in ext for b in ext]
+    A = np.array([_limbs32(v, n) for v in pa], dtype=np.uint32)
+    B = np.array([_limbs32(v, n) for v in pb], dtype=np.uint32)
+    out = np.zeros_like(A)
+    assert emu.emu_fp_op(fid, 8, _p(A), _p(B), _p(out), len(pa)) == 0
+    for i, (a, b) in enumerate(zip(pa, pb)):
+        assert sum(int(out[i, j]) << (32 * j) for j in range(n)) == (a * b * Rinv) % p, (fid, i)
 
 
 @pytest.mark.parametrize("curve", [BLS12_381, BN254, BW6_761], ids=lambda c: c.name)

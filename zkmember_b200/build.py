@@ -45,7 +45,7 @@ def _nvcc() -> str:
     return "nvcc"
 
 
-BASE_HEADERS = ["zkm_common.cuh", "zkm_curve.cuh", "zkm_field.cuh", "zkm_arith.cuh", "zkm_constants.cuh"]
+BASE_HEADERS = ["zkm_common.cuh", "zkm_curve.cuh", "zkm_field.cuh", "zkm_fpmul_u.cuh", "zkm_arith.cuh", "zkm_constants.cuh"]
 UNIT_HEADERS = {
     "zkm_api.cu": [],
     "zkm_ntt_bls.cu": ["zkm_ntt.cuh"],

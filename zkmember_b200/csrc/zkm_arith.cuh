@@ -17,11 +17,13 @@
 #define ZKM_DEV inline
 #define ZKM_CONST_ARRAY(name, n) static const uint32_t name[n]
 #define ZKM_UNROLL
+#define ZKM_CEXPR inline constexpr
 #else
 #define ZKM_HD __host__ __device__ __forceinline__
 #define ZKM_DEV __device__ __forceinline__
 #define ZKM_CONST_ARRAY(name, n) static __device__ __constant__ uint32_t name[n]
 #define ZKM_UNROLL _Pragma("unroll")
+#define ZKM_CEXPR __host__ __device__ __forceinline__ constexpr
 #endif
 
 namespace zkm {

@@ -21,6 +21,7 @@
 #pragma once
 #include "zkm_arith.cuh"
 #include "zkm_constants.cuh"
+#include "zkm_fpmul_u.cuh"
 
 namespace zkm {
 
@@ -30,6 +31,8 @@ namespace zkm {
         static constexpr int N = NLIMBS;                                            \
         static constexpr uint32_t INV = PREFIX##_INV32;                             \
         static constexpr int BITS = PREFIX##_BITS;                                  \
+        static constexpr int UR = PREFIX##_UR;   /* radix bits of the carry-free product */ \
+        static ZKM_CEXPR uint32_t modu(int i) { constexpr uint32_t t[] = PREFIX##_MODU; return t[i]; } \
         static ZKM_DEV uint32_t mod(int i) { return PREFIX##_MOD[i]; }              \
         static ZKM_DEV uint32_t one(int i) { return PREFIX##_ONE[i]; }              \
         static ZKM_DEV uint32_t r2(int i) { return PREFIX##_R2[i]; }                \
@@ -143,9 +146,15 @@ ZKM_DEV Fp<P> fp_dbl(const Fp<P>& a) {
     return fp_add(a, a);
 }
 
-// Montgomery product a*b*R^-1 mod p, fully reduced.
+// Montgomery product a*b*R^-1 mod p, fully reduced: the saturated 32-bit CIOS described above.  This is the
+// product the kernels use (fp_mul below).  Round 2 measured the alternative -- unsaturated radix 2^30 columns of
+// plain IMAD.WIDE.U32 without carry predicates (zkm_fpmul_u.cuh, fp_mul_unsat) -- and found it 0.65-0.9x: on
+// sm_100a EVERY 32x32->64 product issues at ~31 /clk/SM whatever its form (IMAD.WIDE with or without a 64-bit
+// addend, .X carry, IMAD.HI; tools/microbench/int_pipe_peak.cu, profiles/int_pipe_peak_r2.jsonl), so the
+// carry-free schedule only adds ALU instructions.  Both products return identical bytes (host-emulation tests,
+// tools/microbench/fpmul_bench.cu checks 2^20 pairs per field on the device).
 template <class P>
-ZKM_DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+ZKM_DEV Fp<P> fp_mul_cios(const Fp<P>& a, const Fp<P>& b) {
     constexpr int N = P::N;
     static_assert((N & 1) == 0, "even limb count required");
     uint32_t acc[2][2 * N + 2];
@@ -215,9 +224,40 @@ ZKM_DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// Montgomery product on the unsaturated radix (zkm_fpmul_u.cuh): plain IMAD.WIDE products, carries per column.
+// Measured slower than the CIOS on B200 (see above); kept for the microbenchmark and as the cross-check.
+template <class P>
+ZKM_DEV Fp<P> fp_mul_unsat(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> r;
+    fp_mul_u_raw<P>(r.l, fp_split<P>(a.l), fp_split<P>(b.l));
+    fp_final_sub(r);
+    return r;
+}
+// dedicated squaring on the same columns: UM (UM + 1) / 2 products for the a^2 half instead of UM^2
+template <class P>
+ZKM_DEV Fp<P> fp_sqr_unsat(const Fp<P>& a) {
+    Fp<P> r;
+    fp_sqr_u_raw<P>(r.l, fp_split<P>(a.l));
+    fp_final_sub(r);
+    return r;
+}
+
+template <class P>
+ZKM_DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if defined(ZKM_FPMUL_UNSAT)
+    return fp_mul_unsat(a, b);
+#else
+    return fp_mul_cios(a, b);
+#endif
+}
+
 template <class P>
 ZKM_DEV Fp<P> fp_sqr(const Fp<P>& a) {
-    return fp_mul(a, a);
+#if defined(ZKM_FPMUL_UNSAT)
+    return fp_sqr_unsat(a);
+#else
+    return fp_mul_cios(a, a);
+#endif
 }
 
 // a^e for a little-endian multi-limb exponent (setup / normalisation only).
