@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import zkmember_b200 as zkm  # noqa: E402
 from zkmember_b200 import _lib  # noqa: E402
-from oracle import capi  # noqa: E402  (input generator only)
+from oracle import capi, checks  # noqa: E402  (input generator + result checker only, outside the timed regions)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("what", choices=["msm", "ntt"])
@@ -91,6 +91,11 @@ if args.what == "msm":
             t0 = time.perf_counter()
             capi.msm(cid, args.group, hb, h)
             row["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+        # result check of what was timed: known-discrete-log identity, exact big-int arithmetic (oracle/checks.py)
+        rec = d_rec.cpu().numpy().view(np.uint64)
+        k_sum = checks.dlog_sum(h, 0x1234567, 0x89ABCDE, capi.CURVES[cid].fr.modulus)
+        row["check"] = checks.msm_identity_ok(cid, args.group, rec, k_sum)
+        row["check_kind"] = "known-discrete-log identity (exact)"
         row["precompute"] = bool(args.precompute)
         if args.opt:
             row["opts"] = args.opt
@@ -107,6 +112,25 @@ else:
             med, best = timeit(lambda: _lib.check(L.zkm_ntt_device(cid, ctypes.c_void_p(x.data_ptr()),
                                                                    ctypes.c_void_p(y.data_ptr()), lg, inv, cos, sp)), args.reps)
             row[name + "_ms"] = med
+        # result check: every byte against the CPU oracle up to 2^24; above that round trip + Horner spot checks
+        _lib.check(L.zkm_ntt_device(cid, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), lg, 0, 0, sp))
+        torch.cuda.synchronize()
+        if lg <= 24:
+            row["check"] = bool(np.array_equal(y.cpu().numpy().view(np.uint64), capi.ntt(cid, hx)))
+            row["check_kind"] = "fft bytes == CPU oracle"
+        else:
+            z = torch.empty_like(x)
+            _lib.check(L.zkm_ntt_device(cid, ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(z.data_ptr()), lg, 1, 0, sp))
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(z, x))
+            z.zero_()
+            z[:1024] = x[:1024]
+            _lib.check(L.zkm_ntt_device(cid, ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(y.data_ptr()), lg, 0, 0, sp))
+            torch.cuda.synchronize()
+            ev = {k: y[k].cpu().numpy().view(np.uint64) for k in (1, 4097, n - 1)}
+            row["check"] = ok and checks.horner_ok(cid, lg, hx[:1024], ev)
+            row["check_kind"] = "ifft(fft(x)) == x and Horner spot checks (exact)"
+            del z
         row["hbm_frac_fft"] = 2.0 * 8 * capi.fr_words(cid) * n / (row["fft_ms"] * 1e-3) / 6539.9e9
         if args.cpu and lg <= 22:
             import time
