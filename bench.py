@@ -40,10 +40,30 @@ L64 = {0: 6, 1: 4}[CURVE_ID]
 MADS_PER_MODMUL = {0: 300, 1: 136}[CURVE_ID]      # 2 n^2 + n wide MADs, n = 12 / 8 32-bit limbs
 ALGO_MODMULS_PER_POINT = 160                       # ceil(255/16) windows x 10 products (XYZZ mixed add), SURVEY 8d
 METRIC = "G1 MSM 2^%d ms (%s)" % (LOG_N, "BLS12-381" if CURVE_ID == 0 else "BN254")
-# Integer-pipe peak: dependent IMAD.WIDE Montgomery chains measured on this pool's B200 by
-# tools/microbench/imad_peak.cu (profiles/imad_peak_r1.jsonl, modmul_fq384 @ 32 warps/SM).
-IMAD_PEAK_GMADS = 9057.7
-CPU_SAMPLE_LOG_N = int(os.environ.get("ZKM_BENCH_CPU_LOG_N", "21"))
+CPU_LOG_N = int(os.environ.get("ZKM_BENCH_CPU_LOG_N", str(LOG_N)))   # the CPU arm runs the REAL workload size by default
+
+
+def int_pipe_peak():
+    """Integer-pipe peak = the fastest measured issue rate of a 32x32->64 multiply-add on this pool's B200
+    (tools/microbench/int_pipe_peak.cu, profiles/int_pipe_peak_r2.jsonl, SASS in profiles/int_pipe_peak_r2.sass.txt).
+    Every wide form -- IMAD.WIDE.U32 with or without a 64-bit addend, the carry-chained IMAD.WIDE.U32.X, IMAD.HI --
+    issues at ~31 per clock per SM; only the 32-bit IMAD (low half) reaches 61.  Round 1's 17 993 GMAD/s
+    ("imad_wide", profiles/imad_peak_r1.jsonl) was an artefact: ptxas had hoisted the loop-invariant product, the loop
+    measured IADD3 pairs (SASS in the same file)."""
+    best, src = 0.0, None
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "int_pipe_peak_r2.jsonl")):
+            r = json.loads(line)
+            if r.get("bench") in ("mul_wide", "imad_hi", "imad_wide_carry_chain") and r["Gops_s"] > best:
+                best, src = r["Gops_s"], "%s @ %d warps/SM" % (r["sass"], r["warps_per_sm"])
+    except Exception:
+        pass
+    if not best:
+        best, src = 8994.4, "fallback: IMAD.WIDE.U32.X chain, profiles/int_pipe_peak_r2.jsonl as committed"
+    return best, src
+
+
+IMAD_PEAK_GMADS, IMAD_PEAK_SRC = int_pipe_peak()
 
 
 def read_peaks():
@@ -107,52 +127,84 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_run(steps: int, warmup: int, sample_log_n: int):
-    """The arkworks-0.3.0 MSM algorithm (C++ restatement, oracle/cpp) on the host cores."""
+def host_threads() -> int:
+    """Threads the CPU arm uses: every core this process may run on (an inherited OMP_NUM_THREADS=1, as torchrun
+    sets, is ignored: the thread count is passed to the oracle explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline_run(runs: int, log_n: int):
+    """The arkworks-0.3.0 MSM algorithm (C++ restatement, oracle/cpp) on the host cores, on the REAL workload size
+    (2^24 points, ~15-35 s per run depending on the box), `runs` times; nothing is extrapolated."""
     import numpy as np
     from oracle import capi
-    n = 1 << sample_log_n
+    n = 1 << log_n
+    threads = host_threads()
     bases = capi.progression(CURVE_ID, 1, 0x1234567, 0x89ABCDE, n)
-    scal = capi.random_scalars(CURVE_ID, n, seed=0x5EED0000 + sample_log_n)
-    cores = capi.lib().orc_num_threads()
+    scal = capi.random_scalars(CURVE_ID, n, seed=0x5EED0000 + log_n)
     c_bits = capi.msm_window_bits(n)
     bits = 255 if CURVE_ID == 0 else 254
     windows = (bits + c_bits - 1) // c_bits      # window_starts = 0, c, 2c, ... < MODULUS_BITS
     times = []
-    for it in range(warmup + steps):
+    for _ in range(max(1, runs)):
         t0 = time.perf_counter()
-        capi.msm(CURVE_ID, 1, bases, scal)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    scale = (1 << LOG_N) / n
-    return {
-        "value": ms * scale, "unit": "ms", "cores": int(min(cores, windows)), "kind": "port",
-        "sample": "2^%d-point MSM (1/%d of the workload) timed %.1f ms/step with %d OpenMP threads available; arkworks "
-                  "runs one task per window (%d windows at c=%d), value scaled linearly to 2^%d"
-                  % (sample_log_n, int(scale), ms, cores, windows, c_bits, LOG_N),
-        "sample_ms": ms, "host_threads": int(cores),
+        capi.msm(CURVE_ID, 1, bases, scal, threads=threads)
+        times.append((time.perf_counter() - t0) * 1e3)
+    ms = sum(times) / len(times)
+    out = {
+        "value": ms, "unit": "ms", "cores": int(min(threads, windows)), "kind": "port", "runs": len(times),
+        "sample": "the full 2^%d-point MSM, %d run(s), %d threads requested explicitly (arkworks runs one task per window: "
+                  "%d windows at c=%d, so at most %d threads work); arkworks-0.3.0 algorithm restated in C++ (oracle/cpp), "
+                  "not the Rust binary" % (log_n, len(times), threads, windows, c_bits, windows),
+        "host_threads": threads, "run_ms": times,
     }
+    if log_n != LOG_N:
+        out["value"] = ms * (1 << LOG_N) / n
+        out["sample"] += "; ZKM_BENCH_CPU_LOG_N override: value scaled linearly from 2^%d" % log_n
+    return out
+
+
+def cpu_ntt_baseline(log_n: int):
+    """ark-poly's in_order_fft_in_place restated (oracle/cpp), all host threads, the real 2^log_n transform."""
+    from oracle import capi
+    threads = host_threads()
+    x = capi.random_field_elements(CURVE_ID, 1 << log_n, seed=0x5EED1000 + log_n)
+    capi.ntt(CURVE_ID, x[: 1 << 16], threads=threads)          # warm the thread pool
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        capi.ntt(CURVE_ID, x, threads=threads)
+        times.append((time.perf_counter() - t0) * 1e3)
+    return {"value": min(times), "unit": "ms", "cores": threads, "kind": "port", "runs": len(times),
+            "sample": "the full 2^%d transform, best of %d, %d threads" % (log_n, len(times), threads)}
 
 
 def run_reference(args):
+    """--impl reference: the CPU arm alone.  One REAL 2^24 MSM per step; the requested step / warm-up counts are upper
+    bounds (a step costs ~15-35 s of all host cores): at most 2 timed steps and no warm-up, reported as run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, args.steps)
-    warmup = min(args.warmup, 1)
-    base = cpu_baseline_run(steps, warmup, CPU_SAMPLE_LOG_N)
+    steps = max(1, min(args.steps, 2 if CPU_LOG_N >= 23 else 5))
+    t0 = time.perf_counter()
+    base = cpu_baseline_run(steps, CPU_LOG_N)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "ms", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": base["value"], "higher_is_better": False,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u32-limb Montgomery integers", "data": "synthetic",
+        "steps": steps, "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": base["value"], "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64-limb Montgomery integers (CPU)", "data": "synthetic",
         "config": {"workload": "G1 MSM, %s, 2^%d points, uniform scalars; CPU: arkworks-0.3.0 algorithm restated in C++ "
-                               "(oracle/cpp), not the Rust binary" % (CURVE_NAME, LOG_N)},
+                               "(oracle/cpp), not the Rust binary" % (CURVE_NAME, LOG_N),
+                   "note": "steps / warmup are what actually ran: every step is the full 2^%d MSM on all host cores"
+                           % CPU_LOG_N},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "wall_s": None,
     }
+    line["wall_s"] = time.perf_counter() - t0
     print(json.dumps(line))
     return 0
 
@@ -307,10 +359,12 @@ def main():
     zkm.set_option("profile", 1)
     stages = np.zeros(6, dtype=np.float64)
     acc = np.zeros(6, dtype=np.float64)
+    cnt = np.zeros(16, dtype=np.uint64)
     for _ in range(args.steps):
         reg.msm_device(d_scal.data_ptr(), n_local, d_rec.data_ptr(), stream=stream)
         _lib.check(L.zkm_profile_last_msm(ctypes.c_void_p(stages.ctypes.data)))
         acc += stages
+    _lib.check(L.zkm_profile_last_msm_counts(ctypes.c_void_p(cnt.ctypes.data)))
     zkm.set_option("profile", 0)
     acc /= args.steps
     # bucket accumulation = batched-affine pair levels (k_pair_fwd / k_inv_batch / k_pair_bwd) + XYZZ tail
@@ -319,9 +373,27 @@ def main():
     bits = 255 if CURVE_ID == 0 else 254
     windows = (bits + 1 + c_bits - 1) // c_bits    # signed digits: one spare bit for the carry
     algo_mads = ALGO_MODMULS_PER_POINT * n_local * MADS_PER_MODMUL
-    per_entry = 6.5 if acc[1] > 0 else 10.0         # ~6.1 products per affine addition, 10 per XYZZ mixed addition
-    actual_mads = windows * per_entry * n_local * MADS_PER_MODMUL
-    achieved = algo_mads / (accum_ms * 1e-3) / 1e9
+    # EXECUTED field products of the stage, from the device's own counters (zkm_profile_last_msm_counts -- exact list
+    # sizes read back after the run, not estimates) and the per-operation product counts of the kernels' formulas:
+    #   pairwise level : 6 per affine addition (1 in k_pair_fwd: run * d; 5 in k_pair_bwd: run * pre, run * d,
+    #                    num * dinv, lambda^2, lambda * (x0 - x3)); pairs of a level = inputs - outputs;
+    #                    + 3 per thread total and 1 per inversion thread in k_inv_batch (prefix, two unwind products, R^3)
+    #   XYZZ tail      : 10 per mixed addition (madd-2008-s: 8M + 2S); the first entry of a task only loads
+    entries, n_lvl, tasks = int(cnt[3]), int(cnt[12]), int(cnt[13])
+    m_pair, m_inv = 64, 32                           # library defaults (options msm_pair_m / msm_pair_m2)
+    lvl_in, products, pairs_total = entries, 0, 0
+    for l in range(n_lvl):
+        lvl_out = int(cnt[4 + l])
+        pairs = lvl_in - lvl_out
+        n_t = -(-lvl_out // m_pair)
+        products += 6 * pairs + 3 * n_t + -(-n_t // m_inv)
+        pairs_total += pairs
+        lvl_in = lvl_out
+    madds = max(lvl_in - tasks, 0)
+    products += 10 * madds
+    executed_mads = products * MADS_PER_MODMUL
+    achieved = executed_mads / (accum_ms * 1e-3) / 1e9
+    algo_rate = algo_mads / (accum_ms * 1e-3) / 1e9
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
@@ -334,13 +406,15 @@ def main():
         "bound": "int_pipe",
         "achieved": achieved, "peak": IMAD_PEAK_GMADS, "unit": "GMAD/s", "frac": achieved / IMAD_PEAK_GMADS,
         "traffic": traffic, "kernel_ms": accum_ms,
-        "algorithmic": "160 Fq products/point (16 windows x 10 per XYZZ mixed add, SURVEY 8d) x %d wide MADs x %d points"
-                       % (MADS_PER_MODMUL, n_local),
-        "executed_frac": (actual_mads / (accum_ms * 1e-3) / 1e9) / IMAD_PEAK_GMADS,
-        "executed": "%d windows of %d bits x ~%.1f products per entry (estimate)" % (windows, c_bits, per_entry),
-        "note": "frac > 1 is possible: the path executes fewer products than the canonical count (fewer windows, "
-                "affine additions with batched inversion); executed_frac is the pipe utilisation",
-        "peak_source": "measured: dependent IMAD.WIDE Montgomery chains, profiles/imad_peak_r1.jsonl (this pool's B200)",
+        "executed": {"field_products": products, "wide_mads": executed_mads, "list_entries": entries, "affine_levels": n_lvl,
+                     "affine_additions": pairs_total, "xyzz_mixed_additions": madds, "mads_per_product": MADS_PER_MODMUL,
+                     "source": "zkm_profile_last_msm_counts (device counters of this run) x per-formula product counts"},
+        "algorithmic": {"wide_mads": algo_mads, "gmads": algo_rate, "over_peak": algo_rate / IMAD_PEAK_GMADS,
+                        "definition": "SURVEY 8d canonical count: 160 Fq products/point (16 windows x 10 per XYZZ mixed add) x "
+                                      "%d wide MADs x %d points" % (MADS_PER_MODMUL, n_local),
+                        "note": "exceeds the executed work (fewer windows at c=%d, 6-product affine additions with batched "
+                                "inversion), so it can exceed the pipe peak; `frac` is the executed work" % c_bits},
+        "peak_source": "measured: %s (profiles/int_pipe_peak_r2.jsonl, this pool's B200)" % IMAD_PEAK_SRC,
     }
 
     # ---- end to end through the host API
@@ -359,26 +433,36 @@ def main():
         _lib.check(L.zkm_testgen_progression_device(CURVE_ID, 1, a0 + lo * dstep, dstep, n_local,
                                                     ctypes.c_void_p(d_b2.data_ptr()), sp))
         torch.cuda.synchronize()
-        zkm.set_option("msm_precompute", 1)
         t0 = time.perf_counter()
-        reg_pre = zkm.RegisteredBases.from_device(CURVE_ID, 1, d_b2.data_ptr(), n_local)
+        reg_pre = zkm.RegisteredBases.from_device(CURVE_ID, 1, d_b2.data_ptr(), n_local, precompute=True)
         torch.cuda.synchronize()
         reg_s = time.perf_counter() - t0
-        zkm.set_option("msm_precompute", 0)
         if world == 1:
-            # cold call: nothing registered, bases AND scalars cross PCIe inside the timed region
-            # (zkm_msm_g1, the literal multi_scalar_mul(bases, scalars) signature)
+            # the literal multi_scalar_mul(bases, scalars) signature (zkm_msm_g1): HOST bases and HOST scalars.  The first
+            # call uploads the bases (cold); later calls find them in the registration cache (fingerprint of 512 sampled
+            # records per call) -- the proving key is the same vector for every proof (benches/groth16.rs:107-115).
             h_bases = d_b2.cpu().pin_memory()
+            _lib.check(L.zkm_msm_cache_clear())
             cold = []
-            for _ in range(3):
+            for _ in range(4):
                 t1 = time.perf_counter()
                 _lib.check(L.zkm_msm_g1(CURVE_ID, ctypes.c_void_p(h_bases.data_ptr()), ctypes.c_void_p(0),
                                         ctypes.c_void_p(h_scal.data_ptr()), n_local, ctypes.c_void_p(h_out.ctypes.data),
                                         ctypes.c_void_p(h_inf.ctypes.data)))
                 cold.append((time.perf_counter() - t1) * 1e3)
+            e2e["unregistered_first_call_ms"] = cold[0]
             e2e["unregistered_ms"] = min(cold[1:])
-            e2e["unregistered_h2d_bytes"] = int(n_local * (32 + W2 * 8))
+            e2e["unregistered_over_registered"] = min(cold[1:]) / wall_e2e
+            e2e["unregistered_h2d_bytes_first_call"] = int(n_local * (32 + W2 * 8))
             e2e["unregistered_same_result"] = bool(h_out.tobytes() == final[:W2].tobytes())
+            zkm.set_option("msm_cache", 0)
+            t1 = time.perf_counter()
+            _lib.check(L.zkm_msm_g1(CURVE_ID, ctypes.c_void_p(h_bases.data_ptr()), ctypes.c_void_p(0),
+                                    ctypes.c_void_p(h_scal.data_ptr()), n_local, ctypes.c_void_p(h_out.ctypes.data),
+                                    ctypes.c_void_p(h_inf.ctypes.data)))
+            e2e["unregistered_no_cache_ms"] = (time.perf_counter() - t1) * 1e3
+            zkm.set_option("msm_cache", 1)
+            _lib.check(L.zkm_msm_cache_clear())
             del h_bases
         del d_b2
 
@@ -391,7 +475,7 @@ def main():
         ms_pre, _ = timed(step_pre, args.steps, 2)
         final_pre = (d_final if world > 1 else d_rec).cpu().numpy().view(np.uint64)
         pre = {"ms": ms_pre, "register_s": reg_s, "same_result_as_headline": bool(np.array_equal(final_pre, final)),
-               "note": "bases registered with option msm_precompute (table of 2^(c w) P_i, W x the base memory)"}
+               "note": "bases registered with ZKM_REG_PRECOMPUTE (table of 2^(c w) P_i, W x the base memory)"}
         reg_pre.release()
 
     # ---- secondary headline: 2^24 Fr NTT (independent transform per GPU)
@@ -417,14 +501,34 @@ def main():
         # integer-pipe view of the same kernel: (log2 n / 2) Fr products per element x 136 wide MADs
         ntt_mads = 0.5 * LOG_N * n_ntt * 136
         ntt_gmads = ntt_mads / (ms_ntt * 1e-3) / 1e9
+        # end to end: pinned HOST buffer in and out through zkm_ntt (512 MiB each way at 2^24: PCIe-bound)
+        h_x = torch.from_numpy(capi.random_field_elements(CURVE_ID, n_ntt, seed=0x5EED1000 + LOG_N).view(np.int64)).pin_memory()
+        want_head = None
+        def step_ntt_e2e():
+            _lib.check(L.zkm_ntt(CURVE_ID, ctypes.c_void_p(h_x.data_ptr()), LOG_N, 0, 0))
+        h_times = []
+        for it in range(4):
+            t1 = time.perf_counter()
+            step_ntt_e2e()
+            h_times.append((time.perf_counter() - t1) * 1e3)
+        ntt_e2e = {"value": min(h_times[1:]), "unit": "ms", "h2d_bytes_per_step": int(n_ntt * 32), "d2h_bytes_per_step": int(n_ntt * 32),
+                   "note": "zkm_ntt on a pinned host buffer, in place: upload, transform, download (wall clock, best of 3 after a "
+                           "warm-up call)"}
+        del h_x
+        ntt_cpu = None
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            ntt_cpu = cpu_ntt_baseline(LOG_N)
         ntt = {"metric": "Fr NTT 2^%d ms (%s)" % (LOG_N, CURVE_NAME), "ms": ms_ntt,
+               "e2e": ntt_e2e, "cpu_baseline": ntt_cpu,
                "ntts_per_s_all_gpus": world * 1e3 / ms_ntt,
                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                             "algorithmic": "64 B/element (read once + write once)", "traffic": ntt_traffic},
                "int_pipe": {"achieved": ntt_gmads, "peak": IMAD_PEAK_GMADS, "unit": "GMAD/s",
                             "frac": ntt_gmads / IMAD_PEAK_GMADS,
-                            "algorithmic": "log2(n)/2 Fr products per element x 136 wide MADs"},
+                            "algorithmic": "log2(n)/2 Fr products per element x 136 wide MADs (executed: + the four-step and "
+                                           "coset products, ~1 per element per extra pass)",
+                            "peak_source": "measured: %s (profiles/int_pipe_peak_r2.jsonl)" % IMAD_PEAK_SRC},
                "note": "device-resident, out of place; integer-pipe bound on B200 (see DESIGN.md): the HBM fraction "
                        "is reported as the contract asks, int_pipe is the binding roofline"}
         del x, y
@@ -474,7 +578,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = cpu_baseline_run(1, 0, CPU_SAMPLE_LOG_N)
+        cpu = cpu_baseline_run(1, CPU_LOG_N)
 
     if rank == 0:
         line = {

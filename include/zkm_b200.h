@@ -22,11 +22,26 @@
  * calls back.  There is NO CPU fallback: without a usable CUDA device every compute entry point
  * fails with ZKM_ERR_CUDA.
  *
- * Threading: one process per GPU is the intended deployment (zkm_init(device) once, then any
- * thread may call).  Calls on one device are serialised by an internal mutex.
+ * Devices and threading.  zkm_init(device) binds the process to one GPU (the torchrun-style deployment: one process
+ * per GPU); zkm_init_mask(mask) initialises several GPUs of the box for ONE process (the Rust prover is a single
+ * process: /root/reference/benches/groth16.rs:115): bases can then be registered on a chosen device
+ * (ZKM_REG_DEVICE(i), e.g. the G2 query on its own GPU) or sharded over all of them (ZKM_REG_SHARD), and MSMs over
+ * such registrations run on every owning GPU at once, partial sums reduced on the caller's device over NVLink P2P.
+ * Any host thread may call any entry point concurrently.  Every compute call borrows a LANE of the device it runs on
+ * (16 per device: a stream plus grow-only workspaces) for its duration; calls on different lanes overlap on the GPU.
+ * A lane keeps its workspaces until zkm_shutdown(): after a 2^24-point MSM that is ~20 GB on that lane, so a few
+ * concurrent LARGE MSMs can exhaust HBM (they then fail with ZKM_ERR_OOM, nothing is corrupted).
+ * Options (zkm_set_option) are snapshotted when a call starts: changing them never affects a call in flight.
+ *
+ * Device-pointer entry points (`*_device`): pointers must be 16-byte aligned (128-bit vector accesses) and must
+ * belong to an initialised device -- the call runs on the device that owns the OUTPUT pointer.  `stream` is a
+ * cudaStream_t of that device; NULL means a library-owned NON-BLOCKING stream, which does NOT synchronise with the
+ * legacy default stream: the producers of the inputs must have completed (or pass the stream they run on).
  *
  * Ownership: the caller owns every buffer it passes; the library reads inputs / writes outputs
- * during the call only and retains nothing except bases registered with zkm_bases_register*.
+ * during the call only and retains nothing except bases registered with zkm_bases_register* (and, for
+ * zkm_msm_g1/g2, the internal registration cache described there).  zkm_bases_release() may be called while other
+ * threads still use the handle: the memory is freed when the last such call has finished.
  */
 #ifndef ZKM_B200_H
 #define ZKM_B200_H
@@ -53,6 +68,14 @@ extern "C" {
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */
 int32_t zkm_init(int32_t device);   /* bind this process to CUDA device `device`; idempotent */
+/* One process, several GPUs: initialise every device whose bit is set (bit i = CUDA device i); the lowest set bit is
+ * the PRIMARY device (index 0), where host-pointer calls run unless a registration says otherwise.  Idempotent for the
+ * same mask; zkm_init(d) == zkm_init_mask(1u << d).  (`zkm_init(device_mask)`.) */
+int32_t zkm_init_mask(uint32_t device_mask);
+/* Explicit device list (devices[0] = primary).  A CUDA ordinal may be repeated: the entries then act as separate
+ * "devices" with their own lanes on the same GPU -- how the multi-GPU paths are exercised on a one-GPU test box. */
+int32_t zkm_init_devices(const int32_t* devices, int32_t count);
+int32_t zkm_initialised_devices(void);   /* number of entries zkm_init* initialised (0 before) */
 void zkm_shutdown(void);            /* release every device allocation and registered bases */
 const char* zkm_last_error(void);   /* thread-local, never NULL */
 int32_t zkm_device_count(void);     /* visible CUDA devices (0 when none / no driver) */
@@ -64,7 +87,15 @@ const char* zkm_version(void);
  * sum_{i<n} scalars[i] * bases[i] and returns the unique normalised affine point.  The caller has
  * already taken n = min(len(bases), len(scalars)) as upstream does.  Zero scalars and infinity
  * bases are legal; n = 0 gives the identity (out_inf = 1, out_xy = arkworks' zero: x = 0, y = 1).
- * `infinity` may be NULL (no point at infinity among the bases).  All pointers are HOST pointers. */
+ * `infinity` may be NULL (no point at infinity among the bases).  All pointers are HOST pointers.
+ *
+ * Registration cache (option "msm_cache", default 1): the reference calls multi_scalar_mul(bases, scalars) with the
+ * SAME proving-key vectors for every proof (`pk` is created once, /root/reference/benches/groth16.rs:107-115), so for
+ * n >= 1024 the uploaded bases are kept as an internal registration keyed by (curve, group, bases pointer, infinity
+ * pointer, n) and validated by a content fingerprint on every call: 1 = FNV-1a over 512 evenly spaced records (cheap;
+ * assumes the vector is not partially rewritten in place between calls), 2 = over every byte, 0 = no cache (upload
+ * every time).  A fingerprint mismatch re-uploads.  Least-recently-used entries are dropped above
+ * "msm_cache_max_mb" (default 32768). */
 int32_t zkm_msm_g1(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity,
                    const uint64_t* scalars, size_t n, uint64_t* out_xy, uint8_t* out_inf);
 int32_t zkm_msm_g2(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity,
@@ -74,6 +105,14 @@ int32_t zkm_msm_g2(int32_t curve, const uint64_t* bases_xy, const uint8_t* infin
  * /root/reference/benches/groth16.rs:107-115): upload them once and refer to them by handle. */
 int32_t zkm_bases_register(int32_t curve, int32_t group /* 1 | 2 */, const uint64_t* bases_xy,
                            const uint8_t* infinity, size_t n, uint64_t* handle_out);
+/* Registration with flags: */
+#define ZKM_REG_PRECOMPUTE 1u      /* also store the window multiples 2^(c w) P_i (W x the memory): all windows of later
+                                      MSMs share one bucket set, no final doubling chain -- for proving keys / SRS */
+#define ZKM_REG_SHARD 2u           /* split the bases evenly over ALL initialised devices (range sharding) */
+#define ZKM_REG_DEVICE(i) ((uint32_t)((i) + 1) << 8)   /* place the bases on initialised device index i (default 0) */
+/* `bases_xy` / `infinity` may be host pointers or device pointers (of any device). */
+int32_t zkm_bases_register_ex(int32_t curve, int32_t group, const uint64_t* bases_xy, const uint8_t* infinity, size_t n,
+                              uint32_t flags, uint64_t* handle_out);
 int32_t zkm_bases_release(uint64_t handle);
 /* MSM over bases[offset .. offset + n) of a registration (KZG10::commit's powers_of_g[z..] slice,
  * ark-poly-commit 0.3.0 src/kzg10/mod.rs); scalars and outputs are HOST pointers. */
@@ -87,6 +126,25 @@ int32_t zkm_msm_registered(uint64_t handle, size_t offset, const uint64_t* scala
  * low degree first); the zero-skip, into_repr() and the MSM run on the device.  Returns the affine
  * commitment.  The hiding term (a second, small MSM over powers_of_gamma_g) is a second call + one add. */
 int32_t zkm_kzg_commit(uint64_t handle, const uint64_t* coeffs, size_t n, uint64_t* out_xy, uint8_t* out_inf);
+/* All commitments of one prover round in one call (Marlin commits 4 + 3 + 2 polynomials per proof:
+ * /root/reference/benches/marlin.rs:311 -> ark-marlin AHP rounds -> MarlinKZG10::commit): `count` polynomials over the
+ * same powers, committed concurrently on separate lanes.  out_xy: count x 2 W words, out_inf: count flags. */
+int32_t zkm_kzg_commit_batch(uint64_t handle, int32_t count, const uint64_t* const* coeffs, const size_t* n,
+                             uint64_t* out_xy, uint8_t* out_inf);
+/* KZG10::commit WITH its hiding term (ark-poly-commit 0.3.0 src/kzg10/mod.rs: `random_commitment =
+ * multi_scalar_mul(powers_of_gamma_g, random_ints).into_affine(); commitment.add_assign_mixed(&random_commitment)`).
+ * `blinding_coeffs`: the nb coefficients of the caller's blinding polynomial (Montgomery Fr; sampling them is the
+ * caller's RNG, unchanged host code).  Both MSMs run concurrently; returns the affine sum. */
+int32_t zkm_kzg_commit_hiding(uint64_t handle_g, uint64_t handle_gamma_g, const uint64_t* coeffs, size_t n,
+                              const uint64_t* blinding_coeffs, size_t nb, uint64_t* out_xy, uint8_t* out_inf);
+/* KZG10::open (src/kzg10/mod.rs compute_witness_polynomial + open_with_witness_polynomial): the witness polynomial
+ * (p(X) - p(z)) / (X - z) is computed ON THE DEVICE (blocked synthetic division), converted with into_repr and
+ * committed over powers_of_g; with a blinding polynomial (handle_gamma_g != 0, nb > 0) the hiding witness is added and
+ * out_random_v receives blinding_polynomial.evaluate(z) (Montgomery Fr).  `point`: z, one Montgomery Fr element.
+ * Returns Proof.w as an affine point.  out_random_v may be NULL. */
+int32_t zkm_kzg_open(uint64_t handle_g, uint64_t handle_gamma_g, const uint64_t* coeffs, size_t n,
+                     const uint64_t* blinding_coeffs, size_t nb, const uint64_t* point, uint64_t* out_w_xy,
+                     uint8_t* out_w_inf, uint64_t* out_random_v);
 
 /* ---- radix-2 NTT ------------------------------------------------------------------------------
  * Replaces ark_poly::Radix2EvaluationDomain::{fft_in_place, ifft_in_place, coset_fft_in_place,
@@ -128,7 +186,9 @@ int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5xS64);
 int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n,
                        int32_t inverse, int32_t coset, void* stream);
 /* d_out: 2 * W words (affine, Montgomery) followed by one u64 infinity flag (0 | 1).
- * Synchronises once internally (bucket-occupancy read-back that sizes the reduction tree). */
+ * Synchronises once internally (bucket-occupancy read-back that sizes the reduction tree).  If the registration lives
+ * on other devices (ZKM_REG_DEVICE / ZKM_REG_SHARD) the scalar slices and the result records cross NVLink with
+ * peer copies and sharded partial sums are added on the caller's device. */
 int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n,
                                   uint64_t* d_out, void* stream);
 /* `count` independent MSMs over registered bases issued concurrently (one internal host thread, lane and
@@ -153,13 +213,24 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
  * set also store their window multiples 2^(c w) P -- W times the memory, one-time cost -- so that all
  * windows of later MSMs share one bucket set and the final doubling chain disappears; meant for proving
  * keys / SRS that are reused across many proofs), "msm_xarr" (0 | 1: level-0 x-coordinate array, default 1),
- * "msm_prefetch_fwd" / "msm_prefetch_bwd" (L2 prefetch distance of the level-0 gathers, default 0 = off).
+ * "msm_prefetch_fwd" / "msm_prefetch_bwd" (L2 prefetch distance of the level-0 gathers, default 0 = off),
+ * "msm_cache" (0 | 1 | 2) and "msm_cache_max_mb" (registration cache of zkm_msm_g1/g2, see there),
+ * "spread_host_calls" (0 | 1: host-pointer zkm_ntt / zkm_witness_map calls rotate over the initialised devices).
+ * "msm_precompute" is the legacy form of ZKM_REG_PRECOMPUTE (a process-wide switch: prefer the flag).
  * Unknown keys fail with ZKM_ERR_ARG. */
 int32_t zkm_set_option(const char* key, int64_t value);
 /* With option "profile" = 1: device time (ms, CUDA events on the launching stream) of the six stages of
  * the last MSM: bucket sort | batched-affine pair levels | task lists | XYZZ bucket accumulation | folds |
  * window reduction. */
 int32_t zkm_profile_last_msm(double* ms_out6);
+/* Work counters of the same MSM, read back from the device (exact, not estimated): [0] points, [1] windows, [2] window
+ * bits, [3] bucket-list entries (non-zero digits of non-infinity bases), [4..4+L) outputs of each batched-affine level
+ * (pairs added at level l = inputs - outputs), [12] L, [13] XYZZ tasks of the accumulation kernel, [14] buckets,
+ * [15] fold levels.  bench.py derives the executed field products of the bucket accumulation from these. */
+int32_t zkm_profile_last_msm_counts(uint64_t* out16);
+/* registration cache of zkm_msm_g1/g2: drop every entry / {hits, misses, entries, device bytes} */
+int32_t zkm_msm_cache_clear(void);
+int32_t zkm_msm_cache_stats(uint64_t* out4);
 /* Kernel launches issued by this library since the last call with reset != 0. */
 uint64_t zkm_launch_count(int32_t reset);
 /* Window bits the automatic choice uses for an n-point MSM (for reports). */

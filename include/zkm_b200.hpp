@@ -137,14 +137,14 @@ inline GroupAffine<Curve, GROUP> unpack(const std::vector<uint64_t>& out, uint8_
 template <class Curve, int GROUP>
 class RegisteredBases {
 public:
-    RegisteredBases(const std::vector<GroupAffine<Curve, GROUP>>& bases, bool precompute = false) : n_(bases.size()) {
+    // flags: ZKM_REG_PRECOMPUTE | ZKM_REG_SHARD | ZKM_REG_DEVICE(i) -- passed explicitly, never through a process-wide option
+    RegisteredBases(const std::vector<GroupAffine<Curve, GROUP>>& bases, bool precompute = false, uint32_t flags = 0) : n_(bases.size()) {
         std::vector<uint64_t> xy;
         std::vector<uint8_t> inf;
         detail::pack<Curve, GROUP>(bases, n_, xy, inf);
-        if (precompute) check(zkm_set_option("msm_precompute", 1), "zkm_set_option");
-        int32_t rc = zkm_bases_register(Curve::ID, GROUP, xy.data(), inf.data(), n_, &handle_);
-        if (precompute) zkm_set_option("msm_precompute", 0);
-        check(rc, "zkm_bases_register");
+        int32_t rc = zkm_bases_register_ex(Curve::ID, GROUP, xy.data(), inf.data(), n_,
+                                           flags | (precompute ? ZKM_REG_PRECOMPUTE : 0u), &handle_);
+        check(rc, "zkm_bases_register_ex");
     }
     ~RegisteredBases() { if (handle_) zkm_bases_release(handle_); }
     RegisteredBases(const RegisteredBases&) = delete;

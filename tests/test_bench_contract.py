@@ -23,6 +23,18 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert "workload" in j["config"] and "2^24" in j["config"]["workload"]
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "2^13" in cb["sample"] and cb["value"] == j["value"]
+    assert cb["runs"] == j["steps"] == 2 and j["warmup"] == 0 and cb["host_threads"] >= 1
+    # the timed region the line claims (steps x ms_per_step of the sample actually run) fits the wall clock of the run
+    assert sum(cb["run_ms"]) / 1e3 <= j["wall_s"]
+
+
+def test_reference_arm_ignores_an_inherited_single_thread_openmp_setting():
+    """torchrun exports OMP_NUM_THREADS=1 to its children; the CPU arm passes its thread count explicitly."""
+    env = dict(os.environ, ZKM_BENCH_CPU_LOG_N="13", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    assert j["cpu_baseline"]["host_threads"] == len(os.sched_getaffinity(0))
     assert j["e2e"] == {"value": j["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["vs_baseline"] is None                                # BASELINE.md publishes no number for this metric
 

@@ -53,6 +53,7 @@ def _device_random_fr(torch, curve, n, seed):
     x = torch.randint(-(1 << 63), (1 << 63) - 1, (n, S), dtype=torch.int64, device="cuda", generator=g)
     top_bits = (curve.fr.modulus >> (64 * (S - 1))).bit_length() - 1      # strictly below the modulus' top limb
     x[:, S - 1] &= (1 << top_bits) - 1
+    torch.cuda.synchronize()      # the library's own streams are non-blocking: inputs must be complete before the call
     return x
 
 
@@ -75,6 +76,7 @@ def test_ntt_three_pass_roundtrip_horner(zkm, curve, log_n):
     m = 4096
     xs = torch.zeros_like(x)
     xs[:m] = x[:m]
+    torch.cuda.synchronize()
     coeffs = [fr.from_mont(v) for v in capi.limbs_to_ints(x[:m].cpu().numpy().view(np.uint64))]
     d = exact.domain_constants(fr, log_n)
     for coset in (False, True):
@@ -123,6 +125,7 @@ def test_msm_known_discrete_log_full_size(zkm, curve, g, log_n, kind):
         one[0] = 1
         d_s[u < 0.45] = 0
         d_s[(u >= 0.45) & (u < 0.9)] = one
+        torch.cuda.synchronize()
     d_out = torch.zeros(2 * W + 1, dtype=torch.int64, device="cuda")
     reg.msm_device(d_s.data_ptr(), n, d_out.data_ptr())
     torch.cuda.synchronize()

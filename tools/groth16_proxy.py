@@ -63,11 +63,9 @@ inf = {k: np.zeros(sizes[k], dtype=np.uint8) for k in KEYS}
 for k in ("b_g1", "b_g2"):
     inf[k][rng.random(sizes[k]) < 0.5] = 1
 inf["a"][rng.random(n) < 0.1] = 1
-if not args.no_precompute:
-    zkm.set_option("msm_precompute", 1)
 t0 = time.perf_counter()
-regs = {k: zkm.RegisteredBases(cid, 2 if k == "b_g2" else 1, host_bases[k], inf[k]) for k in KEYS}
-zkm.set_option("msm_precompute", 0)
+regs = {k: zkm.RegisteredBases(cid, 2 if k == "b_g2" else 1, host_bases[k], inf[k], precompute=not args.no_precompute)
+        for k in KEYS}
 reg_s = time.perf_counter() - t0
 
 # ---- per-proof inputs (host, pinned; the same values for every proof)

@@ -76,10 +76,7 @@ t0 = time.perf_counter()
 d_srs = torch.empty((n_srs, 2 * W1), dtype=torch.int64, device=dev)
 _lib.check(L.zkm_testgen_progression_device(cid, 1, 0x51D5, 0x7, n_srs, ctypes.c_void_p(d_srs.data_ptr()), sp))
 torch.cuda.synchronize()
-if args.precompute:
-    zkm.set_option("msm_precompute", 1)
-powers = zkm.RegisteredBases.from_device(cid, 1, d_srs.data_ptr(), n_srs)
-zkm.set_option("msm_precompute", 0)
+powers = zkm.RegisteredBases.from_device(cid, 1, d_srs.data_ptr(), n_srs, precompute=args.precompute)
 reg_s = time.perf_counter() - t0
 
 # ---- polynomials (host, Montgomery Fr) and transform buffers (device)

@@ -72,10 +72,7 @@ if args.what == "msm":
     d_rec = torch.zeros(2 * W + 1, dtype=torch.int64, device=dev)
     for lg in range(args.min, args.max + 1):
         n = 1 << lg
-        if args.precompute:
-            zkm.set_option("msm_precompute", 1)
-        reg = zkm.RegisteredBases.from_device(cid, args.group, d_bases.data_ptr(), n)   # first n bases
-        zkm.set_option("msm_precompute", 0)
+        reg = zkm.RegisteredBases.from_device(cid, args.group, d_bases.data_ptr(), n, precompute=args.precompute)   # first n bases
         h = capi.random_scalars(cid, n, seed=0x5EED0000 + lg, kind=args.kind)
         d_s = torch.from_numpy(h.view(np.int64)).to(dev)
         zkm.set_option("profile", 1)

@@ -31,7 +31,18 @@ SYMBOLS = [
     "zkm_ntt", "zkm_domain_constants", "zkm_ntt_device", "zkm_msm_registered_device",
     "zkm_bases_register_device", "zkm_points_sum_device", "zkm_set_option", "zkm_launch_count",
     "zkm_msm_window_bits", "zkm_testgen_progression_device", "zkm_profile_last_msm", "zkm_witness_map", "zkm_witness_map_device", "zkm_fr_into_repr_device", "zkm_kzg_commit", "zkm_msm_batch_registered_device",
+    "zkm_init_mask", "zkm_init_devices", "zkm_initialised_devices", "zkm_bases_register_ex", "zkm_kzg_commit_batch",
+    "zkm_kzg_commit_hiding", "zkm_kzg_open", "zkm_profile_last_msm_counts", "zkm_msm_cache_clear", "zkm_msm_cache_stats",
 ]
+
+# zkm_bases_register_ex flags (include/zkm_b200.h)
+REG_PRECOMPUTE = 1
+REG_SHARD = 2
+
+
+def REG_DEVICE(i: int) -> int:
+    return (int(i) + 1) << 8
+
 
 
 class ZkmError(RuntimeError):
@@ -61,6 +72,14 @@ def load():
     u64p, u8p, vp = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
     i32, u32, sz, u64 = ctypes.c_int32, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint64
     L.zkm_init.argtypes = [i32]
+    L.zkm_init_mask.argtypes = [u32]
+    L.zkm_init_devices.argtypes = [ctypes.c_void_p, i32]
+    L.zkm_bases_register_ex.argtypes = [i32, i32, u64p, u8p, sz, u32, ctypes.POINTER(u64)]
+    L.zkm_kzg_commit_batch.argtypes = [u64, i32, ctypes.c_void_p, ctypes.c_void_p, u64p, u8p]
+    L.zkm_kzg_commit_hiding.argtypes = [u64, u64, u64p, sz, u64p, sz, u64p, u8p]
+    L.zkm_kzg_open.argtypes = [u64, u64, u64p, sz, u64p, sz, u64p, u64p, u8p, u64p]
+    L.zkm_profile_last_msm_counts.argtypes = [ctypes.c_void_p]
+    L.zkm_msm_cache_stats.argtypes = [ctypes.c_void_p]
     L.zkm_shutdown.restype = None
     L.zkm_last_error.restype = ctypes.c_char_p
     L.zkm_version.restype = ctypes.c_char_p
@@ -100,17 +119,28 @@ def check(rc: int):
     raise ZkmError(rc, msg)
 
 
-def init(device: int | None = None):
-    """Bind this process to one GPU (default: LOCAL_RANK, else 0) -- one process per GPU."""
+def init(device=None):
+    """Bind this process to one GPU (default: LOCAL_RANK, else 0) -- one process per GPU -- or, given a list of CUDA
+    ordinals, to several GPUs of the box (one process, many GPUs: `zkm_init_devices`; the first entry is the primary
+    device; a repeated ordinal gives separate lane sets on the same GPU, used to test the sharded paths on one GPU)."""
     global _inited_device
     L = load()
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
-    if _inited_device == device:
+    key = tuple(device) if isinstance(device, (list, tuple)) else int(device)
+    if _inited_device == key:
         return L
-    check(L.zkm_init(device))
-    _inited_device = device
+    if isinstance(key, tuple):
+        arr = (ctypes.c_int32 * len(key))(*key)
+        check(L.zkm_init_devices(ctypes.cast(arr, ctypes.c_void_p), len(key)))
+    else:
+        check(L.zkm_init(key))
+    _inited_device = key
     return L
+
+
+def initialised_devices() -> int:
+    return int(load().zkm_initialised_devices())
 
 
 def lib():

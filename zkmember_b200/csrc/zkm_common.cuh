@@ -8,6 +8,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -91,14 +92,26 @@ struct PinnedBuf {
     }
 };
 
-struct BasesReg {
-    int curve, group;
-    size_t n;
+// One contiguous run of registered bases living on one device.
+struct BasesPart {
+    int dev = 0;              // index into the initialised device list (0 = primary)
+    int ordinal = 0;          // CUDA ordinal of that device (needed to free the memory after shutdown)
+    size_t first = 0, n = 0;  // bases [first, first + n) of the registration
     void* d_xy = nullptr;     // n affine records, 2 * W * 8 bytes each
     uint8_t* d_inf = nullptr; // n flags or nullptr
-    // optional window multiples (option "msm_precompute" at registration): table[w * n + i] = 2^(pre_c w) P_i
+    // optional window multiples (ZKM_REG_PRECOMPUTE): table[w * n + i] = 2^(pre_c w) P_i
     void* d_table = nullptr;
     int pre_c = 0, pre_W = 0;
+};
+// A registration: one part (the usual case), or one part per device when registered with ZKM_REG_SHARD.
+// Held by shared_ptr: zkm_bases_release drops the registry's reference, the memory goes when the last
+// call that looked the handle up has finished.
+struct BasesReg {
+    int curve = 0, group = 0;
+    size_t n = 0;
+    std::vector<BasesPart> parts;
+    size_t bytes = 0;         // device bytes held (registration cache accounting)
+    ~BasesReg();
 };
 
 struct Options {
@@ -106,7 +119,7 @@ struct Options {
     int msm_chunk = 0;
     int ntt_max_radix_log = 12;
     int profile = 0;  // record CUDA events at the MSM stage boundaries
-    int msm_precompute = 0;  // registrations made while set carry precomputed window multiples
+    int msm_precompute = 0;  // legacy switch: registrations made while set behave as if ZKM_REG_PRECOMPUTE was passed
     int msm_affine_levels = -1;  // batched-affine pairwise levels before the XYZZ tasks (-1 = automatic)
     int msm_pair_m = 64, msm_pair_m2 = 32;  // outputs per thread / totals per inversion thread in the pair levels
     // L2 prefetch distance (pairs ahead) of the level-0 gathers; 0 = off.  Measured on B200 at 2^24: every setting
@@ -115,34 +128,33 @@ struct Options {
     int msm_prefetch_fwd = 0, msm_prefetch_bwd = 0;
     int msm_xarr = 1;            // level-0 forward pass gathers x from an array of 64-byte slots (48-byte coordinates)
     int msm_fold = 0;            // fan-in of the XYZZ fold levels (0 = automatic: 4 for small MSMs, 16 for large)
+    // zkm_msm_g1 / zkm_msm_g2 (the literal multi_scalar_mul(bases, scalars) signature): keep the uploaded bases as an
+    // internal registration keyed by (host pointer, n, content fingerprint).  0 = off, 1 = fingerprint of 512 sampled
+    // records (default: proving keys / SRS are immutable while a prover runs), 2 = fingerprint of every byte.
+    int msm_cache = 1;
+    int64_t msm_cache_max_mb = 32768;   // cached registrations are evicted least-recently-used above this
+    int spread_host_calls = 0;   // host-pointer NTT / witness-map calls rotate over the initialised devices
 };
 
-// State shared by all lanes of the process (one process per GPU).
+// State of one initialised device.
 struct Shared {
-    int device = -1;
+    int device = -1;                       // CUDA ordinal
+    int index = 0;                         // position in the initialised device list
     int sm_count = 148;
-    Options opt;
     std::mutex tw_mu;                      // guards `twiddles`
     std::map<uint64_t, void*> twiddles;    // key -> device table (twiddles, coset powers, domain constants)
-    std::mutex reg_mu;                     // guards `bases` / `next_handle`
-    std::map<uint64_t, BasesReg> bases;
-    uint64_t next_handle = 1;
 };
 
-// A lane = one stream + one set of workspaces.  Every compute call borrows a free lane for its duration,
-// so independent calls from different host threads (e.g. the five MSMs of a Groth16 proof, the G2 MSM next
+// A lane = one stream + one set of workspaces on one device.  Every compute call borrows a free lane for its
+// duration, so independent calls from different host threads (e.g. the five MSMs of a Groth16 proof, the G2 MSM next
 // to the G1 ones) run concurrently on the GPU instead of queueing behind one another's serial tails.
 struct Context {
     Shared* sh;
     int& device;
     int& sm_count;
-    Options& opt;
+    Options opt;                           // snapshot taken when the lane was acquired: stable for the whole call
     std::map<uint64_t, void*>& twiddles;
-    std::map<uint64_t, BasesReg>& bases;
-    uint64_t& next_handle;
-    explicit Context(Shared* s)
-        : sh(s), device(s->device), sm_count(s->sm_count), opt(s->opt), twiddles(s->twiddles), bases(s->bases),
-          next_handle(s->next_handle) {}
+    explicit Context(Shared* s) : sh(s), device(s->device), sm_count(s->sm_count), twiddles(s->twiddles) {}
     int lane_id = 0;
     bool busy = false;
     cudaStream_t stream = nullptr;
@@ -150,15 +162,19 @@ struct Context {
     DevBuf ntt_a, ntt_b;
     DevBuf ws[40];
     DevBuf io_scalars, io_bases, io_inf, io_out;
+    DevBuf gather;                         // partial result records of a sharded MSM, summed on this (home) device
     PinnedBuf pin_in, pin_out;
     // stage timing of the last MSM on this lane (opt.profile): events at the boundaries of
     // sort | affine pair levels | task lists | bucket accumulation | fold levels | window reduction
     cudaEvent_t pev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool pev_valid = false;
+    // work counters of the last profiled MSM (device words read back after the run): see zkm_profile_last_msm_counts
+    uint64_t pcount[16] = {0};
     // The lane's workspaces may still be in use by kernels enqueued on the stream of its previous borrower:
     // every call orders itself after `done_ev` and re-records it when it has enqueued its work.
     cudaEvent_t done_ev = nullptr;
     cudaEvent_t sync_ev = nullptr;   // blocking-sync event for host waits while many lanes are busy
+    cudaEvent_t spin_ev = nullptr;   // spinning event for the fold-depth read-back
     void begin(cudaStream_t s) {
         if (done_ev) ZKM_CUDA(cudaStreamWaitEvent(s, done_ev, 0));
     }
@@ -167,14 +183,33 @@ struct Context {
         ZKM_CUDA(cudaEventRecord(done_ev, s));
     }
 };
+// begin()/end() bracket of a call that enqueues on `s`: end() also runs when the call throws after kernels were
+// queued (otherwise the next borrower of the lane could overwrite workspaces that are still in use); if even
+// recording the event fails the stream is drained instead.
+struct StreamScope {
+    Context* c;
+    cudaStream_t s;
+    StreamScope(Context* c_, cudaStream_t s_) : c(c_), s(s_) { c->begin(s); }
+    ~StreamScope() {
+        try {
+            c->end(s);
+        } catch (...) {
+            cudaStreamSynchronize(s);
+            cudaGetLastError();
+        }
+    }
+    StreamScope(const StreamScope&) = delete;
+    StreamScope& operator=(const StreamScope&) = delete;
+};
 
 constexpr int ZKM_NUM_LANES = 16;
-Context* acquire_lane();           // blocks until a lane is free; throws ZKM_ERR_NOT_INIT before zkm_init
+Context* acquire_lane(int dev = 0);  // blocks until a lane of device index `dev` is free; throws ZKM_ERR_NOT_INIT before zkm_init
 void release_lane(Context* c);
 int busy_lane_count();
+int device_count_initialised();
 struct LaneGuard {
     Context* c;
-    LaneGuard() : c(acquire_lane()) {}
+    explicit LaneGuard(int dev = 0) : c(acquire_lane(dev)) {}
     ~LaneGuard() { release_lane(c); }
     LaneGuard(const LaneGuard&) = delete;
     LaneGuard& operator=(const LaneGuard&) = delete;
@@ -203,13 +238,16 @@ void fr_into_repr_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
 void witness_map_run(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
                      cudaStream_t stream);
 void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
-             size_t n, uint64_t* d_out, cudaStream_t stream, const BasesReg* pre = nullptr, size_t pre_offset = 0);
-void msm_precompute(Context* c, BasesReg* reg, cudaStream_t stream);
+             size_t n, uint64_t* d_out, cudaStream_t stream, const BasesPart* pre = nullptr, size_t pre_offset = 0);
+void msm_precompute(Context* c, int curve, int group, BasesPart* part, cudaStream_t stream);
+void kzg_quotient_run(Context* c, int curve, const uint64_t* d_coeffs, size_t n, const uint64_t* d_point, uint64_t* d_quot,
+                      uint64_t* d_eval, cudaStream_t stream);
 void points_sum_run(Context* c, int curve, int group, const uint64_t* d_points, size_t m, uint64_t* d_out,
                     cudaStream_t stream);
 void testgen_progression(Context* c, int curve, int group, uint64_t a0, uint64_t d, size_t n, uint64_t* d_out,
                          cudaStream_t stream);
 int msm_auto_window_bits(int curve, int group, size_t n);
+void note_profiled_lane(Context* c);   // zkm_profile_last_msm* report the lane that ran the last profiled MSM
 
 // 128-bit vectorised global access for field elements (N is a multiple of 4 limbs)
 template <class P>

@@ -265,25 +265,25 @@ static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t
     ZKM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)count, s));
 }
 
-// Window multiples for a registration of n bases: picks the window size once (it is then fixed for every
-// MSM over this registration) and fills reg->d_table.
-void msm_precompute(Context* c, BasesReg* reg, cudaStream_t s) {
-    const CurveOps* ops = curve_ops(reg->curve, reg->group);
-    if (reg->n == 0) return;
-    int cb = c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : auto_window_bits(reg->curve, reg->group, reg->n, 1);
+// Window multiples for one part of a registration: picks the window size once (it is then fixed for every
+// MSM over this part) and fills part->d_table.
+void msm_precompute(Context* c, int curve, int group, BasesPart* part, cudaStream_t s) {
+    const CurveOps* ops = curve_ops(curve, group);
+    if (part->n == 0) return;
+    int cb = c->opt.msm_window_bits > 0 ? c->opt.msm_window_bits : auto_window_bits(curve, group, part->n, 1);
     if (cb < 2) cb = 2;
     if (cb > 24) cb = 24;
     int W = windows_for(ops->scalar_bits, cb);
-    if ((double)reg->n * W >= 2.0e9) ZKM_FAIL(ZKM_ERR_ARG, "precomputed table of %zu x %d points exceeds 2^31 entries", reg->n, W);
-    const size_t rec = 2 * (size_t)coord_words(reg->curve, reg->group) * 8;
-    ZKM_CUDA(cudaMalloc(&reg->d_table, reg->n * (size_t)W * rec));
-    ops->precompute(s, reg->d_xy, reg->d_inf, (uint64_t)reg->n, cb, W, reg->d_table);
-    reg->pre_c = cb;
-    reg->pre_W = W;
+    if ((double)part->n * W >= 2.0e9) ZKM_FAIL(ZKM_ERR_ARG, "precomputed table of %zu x %d points exceeds 2^31 entries", part->n, W);
+    const size_t rec = 2 * (size_t)coord_words(curve, group) * 8;
+    ZKM_CUDA(cudaMalloc(&part->d_table, part->n * (size_t)W * rec));
+    ops->precompute(s, part->d_xy, part->d_inf, (uint64_t)part->n, cb, W, part->d_table);
+    part->pre_c = cb;
+    part->pre_W = W;
 }
 
 void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
-             size_t n, uint64_t* d_out, cudaStream_t s, const BasesReg* pre, size_t pre_offset) {
+             size_t n, uint64_t* d_out, cudaStream_t s, const BasesPart* pre, size_t pre_offset) {
     const CurveOps* ops = curve_ops(curve, group);
     if (n == 0) {
         ops->write_identity(s, d_out);
@@ -348,6 +348,9 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     uint32_t* h_flags = (uint32_t*)c->pin_out.get(64);
 
     const bool prof = c->opt.profile != 0;
+    // work counters of a profiled run (zkm_profile_last_msm_counts): device words read back after the run
+    const uint32_t* cnt_words[16] = {nullptr};
+    int n_cnt_levels = 0;
     auto mark = [&](int i) {
         if (!prof) return;
         if (!c->pev[i]) ZKM_CUDA(cudaEventCreate(&c->pev[i]));
@@ -444,6 +447,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
                           c->opt.msm_prefetch_fwd, lvl == 0 ? xarr : nullptr);
             ops->pair_inv((unsigned)c->sm_count, nU, s, aoff, K, m, m2, Tt, pre2);
             ops->pair_bwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt, pt, c->opt.msm_prefetch_bwd);
+            if (n_cnt_levels < 8) cnt_words[4 + n_cnt_levels++] = aoff + K;   // outputs of this level
             cur_off = aoff;
             cur_cnt = alen;
             cur_src = pt;
@@ -456,30 +460,20 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     // level-1 task list
     ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, cur_cnt, K, L1, tpb[0], flags);
     exclusive_scan(c, tpb[0], tbase[0], K + 1, s);
+    if (prof) ZKM_CUDA(cudaMemcpyAsync(flags + 2, tbase[0] + K, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));  // level-1 task count
     ZKM_CUDA(cudaMemcpyAsync(h_flags, flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     // The one host read-back: largest bucket -> depth of the fold tree.  Only the fold loop needs it, so the event is
     // recorded right after the copy and waited for AFTER the level-1 task list and the bucket accumulation have been
     // enqueued: the GPU keeps working through the host round trip instead of idling behind it.  A spinning wait is
     // the fastest when few calls are in flight; with many concurrent lanes (batched proofs) the spinning host threads
     // starve each other, so they block on an event instead.
-    static cudaEvent_t spin_ev[ZKM_NUM_LANES] = {};   // per lane (a lane has one borrower at a time)
-    static int spin_dev[ZKM_NUM_LANES] = {};
     cudaEvent_t fev;
     if (busy_lane_count() > 6) {
         if (!c->sync_ev) ZKM_CUDA(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         fev = c->sync_ev;
     } else {
-        const int li = c->lane_id % ZKM_NUM_LANES;
-        cudaEvent_t& e = spin_ev[li];
-        if (e && spin_dev[li] != c->device) {       // re-initialised on another device
-            cudaEventDestroy(e);
-            e = nullptr;
-        }
-        if (!e) {
-            ZKM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            spin_dev[li] = c->device;
-        }
-        fev = e;
+        if (!c->spin_ev) ZKM_CUDA(cudaEventCreateWithFlags(&c->spin_ev, cudaEventDisableTiming));
+        fev = c->spin_ev;
     }
     ZKM_CUDA(cudaEventRecord(fev, s));
 
@@ -501,6 +495,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     if (h_flags[1])
         ZKM_FAIL(ZKM_ERR_SCALAR_RANGE, "a scalar has bits at or above bit %d (not a canonical Fr)", pl.scalar_bits + 1);
     const uint32_t maxcnt = h_flags[0];
+    int n_folds = 0;
     int cur = 0;  // tpb[cur] / tbase[cur] / part[cur] describe the current partial sums
     uint32_t maxseg = (maxcnt + L1 - 1) / L1;
     while (maxseg > 1) {
@@ -511,6 +506,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         ops->accum_xyzz(grid_acc, s, part[cur], TaskList{tstart, tlen, order, tbase[nxt], K}, part[nxt],
                         entries < ((size_t)4 << 20) ? 1 : 0);   // small MSM: latency-bound folds, four lanes per chain
         cur = nxt;
+        n_folds++;
         maxseg = (maxseg + L2 - 1) / L2;
     }
 
@@ -520,6 +516,27 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     ops->reduce(s, part[cur], tbase[cur], tpb[cur], pl, contrib, wsum, d_out);
     mark(6);
     c->pev_valid = prof;
+    if (prof) {
+        // [0] points, [1] windows, [2] window bits, [3] list entries (non-zero digits), [4..4+L) outputs of each
+        // batched-affine level, [12] affine levels L, [13] level-1 XYZZ tasks, [14] buckets K, [15] fold levels
+        for (auto& v : c->pcount) v = 0;
+        cnt_words[3] = off + K;
+        cnt_words[13] = flags + 2;
+        ZKM_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < 16; i++) {
+            if (!cnt_words[i]) continue;
+            uint32_t w = 0;
+            ZKM_CUDA(cudaMemcpy(&w, cnt_words[i], sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            c->pcount[i] = w;
+        }
+        c->pcount[0] = n;
+        c->pcount[1] = (uint64_t)pl.W;
+        c->pcount[2] = (uint64_t)pl.c;
+        c->pcount[12] = (uint64_t)n_cnt_levels;
+        c->pcount[14] = K;
+        c->pcount[15] = (uint64_t)n_folds;
+        note_profiled_lane(c);
+    }
 }
 
 void points_sum_run(Context* c, int curve, int group, const uint64_t* d_points, size_t m, uint64_t* d_out,

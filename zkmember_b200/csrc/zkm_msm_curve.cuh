@@ -460,19 +460,21 @@ struct OpsImpl {
     }
     // persistent grids: exactly the co-resident CTAs (or fewer when the level is small)
     template <class K>
-    static unsigned pair_grid(K kernel, int block, unsigned sm_count, uint64_t threads_needed, int* cache) {
-        if (*cache == 0) {
-            ZKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(cache, kernel, block, 0));
-            if (*cache < 1) *cache = 1;
+    static unsigned pair_grid(K kernel, int block, unsigned sm_count, uint64_t threads_needed, std::atomic<int>* cache) {
+        int occ = cache->load(std::memory_order_acquire);     // written from concurrent lanes: same value, atomically
+        if (occ == 0) {
+            ZKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0));
+            if (occ < 1) occ = 1;
+            cache->store(occ, std::memory_order_release);
         }
         uint64_t need = (threads_needed + block - 1) / block;
-        uint64_t cap = (uint64_t)sm_count * (unsigned)*cache;
+        uint64_t cap = (uint64_t)sm_count * (unsigned)occ;
         return (unsigned)(need < cap ? (need ? need : 1) : cap);
     }
     static void pair_fwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
                          const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, int pf,
                          const void* xarr) {
-        static int occ0 = 0, occ1 = 0;
+        static std::atomic<int> occ0{0}, occ1{0};
         if (level0) {
             unsigned grid = pair_grid(k_pair_fwd<F, true>, 256, sm_count, nT_bound, &occ0);
             ZKM_LAUNCH((k_pair_fwd<F, true>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T, pf, (const char*)xarr);
@@ -489,14 +491,14 @@ struct OpsImpl {
     }
     static void pair_inv(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
                          uint32_t m2, void* T, void* pre2) {
-        static int occ = 0;
+        static std::atomic<int> occ{0};
         unsigned grid = pair_grid(k_inv_batch<F>, 128, sm_count, nU_bound, &occ);
         ZKM_LAUNCH(k_inv_batch<F>, grid, 128, 0, s, off_out, K, m, m2, (char*)T, (char*)pre2);
     }
     static void pair_bwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
                          const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre,
                          const void* Tinv, void* dst, int pf) {
-        static int occ0 = 0, occ1 = 0;
+        static std::atomic<int> occ0{0}, occ1{0};
         if (level0) {
             unsigned grid = pair_grid(k_pair_bwd<F, true>, 128, sm_count, nT_bound, &occ0);
             ZKM_LAUNCH((k_pair_bwd<F, true>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst, pf);

@@ -357,6 +357,114 @@ __global__ void k_vanishing_inv(uint32_t* out, int k) {
     st_fp<P>(out, fp_inv(fp_sub(g, Fp<P>::one())));
 }
 
+// ---------------------------------------------------------------------------------- KZG10 witness polynomial
+// q(X) = (p(X) - p(z)) / (X - z): the division KZG10::open performs before its MSM (ark-poly-commit 0.3.0
+// src/kzg10/mod.rs compute_witness_polynomial = p / (X - point); reached from /root/reference/benches/marlin.rs:311
+// through MarlinKZG10::open).  Synthetic division is the recurrence q_{i-1} = p_i + z q_i; here it is evaluated as
+// a blocked scan: with H_c = sum_{j >= c L} p_j z^(j - c L) the value at every chunk boundary,
+//   k_quot_chunk_sums   S_c = sum_{j < L} p_{cL + j} z^j                       one thread per chunk of L coefficients
+//   k_quot_boundaries   H_c = S_c + z^L H_{c+1}  for all c                     one CTA: serial inside a thread's run of
+//                                                                              chunks, Hillis-Steele suffix scan across threads
+//   k_quot_fill         q_i, i in chunk c, by the recurrence started from H_{c+1}
+// H_0 = p(z) comes for free (the evaluation KZG10::open needs of the blinding polynomial).  Exact field arithmetic:
+// the quotient is unique, so the bytes equal upstream's DensePolynomial division.
+constexpr int ZKM_QUOT_L = 32;
+constexpr int ZKM_QUOT_T = 512;
+
+template <class P>
+__global__ void __launch_bounds__(256) k_quot_chunk_sums(const uint32_t* __restrict__ p, uint64_t n, const uint32_t* __restrict__ zp,
+                                                         uint32_t* __restrict__ S, uint64_t nchunks) {
+    const Fp<P> z = ld_fp<P>(zp);
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
+        Fp<P> acc = Fp<P>::zero();
+        const uint64_t lo = c * ZKM_QUOT_L;
+        for (int j = ZKM_QUOT_L - 1; j >= 0; j--) {
+            acc = fp_mul(acc, z);
+            if (lo + j < n) acc = fp_add(acc, ld_fp<P>(p + (lo + j) * P::N));
+        }
+        st_fp<P>(S + c * P::N, acc);
+    }
+}
+
+// S (padded with zeros to ZKM_QUOT_T * per chunks) -> H[c] for c in [0, nchunks]; H[nchunks] = 0
+template <class P>
+__global__ void __launch_bounds__(ZKM_QUOT_T) k_quot_boundaries(const uint32_t* __restrict__ S, uint64_t nchunks, uint64_t per,
+                                                                const uint32_t* __restrict__ zp, uint32_t* __restrict__ H) {
+    extern __shared__ uint4 quot_smem[];
+    uint32_t* A = reinterpret_cast<uint32_t*>(quot_smem);
+    const uint32_t t = threadIdx.x;
+    Fp<P> zL = ld_fp<P>(zp);
+    for (int i = 1; i < ZKM_QUOT_L; i <<= 1) zL = fp_sqr(zL);            // z^L, L a power of two
+    const uint64_t c0 = (uint64_t)t * per;
+    // A_t = sum_{c in own run} S_c zL^(c - c0)
+    Fp<P> acc = Fp<P>::zero();
+    for (uint64_t i = per; i-- > 0;) {
+        acc = fp_mul(acc, zL);
+        if (c0 + i < nchunks) acc = fp_add(acc, ld_fp_plain<P>(S + (c0 + i) * P::N));
+    }
+    st_fp<P>(A + t * P::N, acc);
+    Fp<P> pd = fp_pow_u64(zL, per);                                      // weight of one run; squared every step
+    __syncthreads();
+    for (uint32_t d = 1; d < ZKM_QUOT_T; d <<= 1) {
+        Fp<P> other = Fp<P>::zero();
+        const bool has = t + d < ZKM_QUOT_T;
+        if (has) other = ld_fp_plain<P>(A + (t + d) * P::N);
+        __syncthreads();
+        if (has) {
+            acc = fp_add(acc, fp_mul(pd, other));
+            st_fp<P>(A + t * P::N, acc);
+        }
+        pd = fp_sqr(pd);
+        __syncthreads();
+    }
+    // acc = H at the bottom of the own run; walk the run top-down from the run above
+    Fp<P> v = (t + 1 < ZKM_QUOT_T) ? ld_fp_plain<P>(A + (t + 1) * P::N) : Fp<P>::zero();
+    for (uint64_t i = per; i-- > 0;) {
+        const uint64_t c = c0 + i;
+        if (c + 1 <= nchunks) st_fp<P>(H + (c + 1) * P::N, v);          // v == H_{c+1} here
+        Fp<P> sc = (c < nchunks) ? ld_fp_plain<P>(S + c * P::N) : Fp<P>::zero();
+        v = fp_add(sc, fp_mul(zL, v));
+    }
+    if (t == 0) st_fp<P>(H, v);                                          // H_0 = p(z)
+}
+
+template <class P>
+__global__ void __launch_bounds__(256) k_quot_fill(const uint32_t* __restrict__ p, uint64_t n, const uint32_t* __restrict__ zp,
+                                                   const uint32_t* __restrict__ H, uint32_t* __restrict__ q, uint64_t nchunks) {
+    const Fp<P> z = ld_fp<P>(zp);
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
+        Fp<P> v = ld_fp_plain<P>(H + (c + 1) * P::N);
+        const uint64_t lo = c * ZKM_QUOT_L;
+        for (int j = ZKM_QUOT_L - 1; j >= 0; j--) {
+            const uint64_t i = lo + j;
+            if (i >= n) continue;                                        // beyond the top coefficient: v stays 0
+            if (i + 1 < n) st_fp<P>(q + i * P::N, v);                    // q has n - 1 coefficients
+            v = fp_add(ld_fp<P>(p + i * P::N), fp_mul(z, v));
+        }
+    }
+}
+
+template <class P>
+static void kzg_quotient_t(Context* c, const uint64_t* d_coeffs, size_t n, const uint64_t* d_point, uint64_t* d_quot,
+                           uint64_t* d_eval, cudaStream_t s) {
+    if (n == 0) {
+        if (d_eval) ZKM_CUDA(cudaMemsetAsync(d_eval, 0, P::N * 4, s));
+        return;
+    }
+    const uint64_t nchunks = (n + ZKM_QUOT_L - 1) / ZKM_QUOT_L;
+    const uint64_t per = (nchunks + ZKM_QUOT_T - 1) / ZKM_QUOT_T;
+    uint32_t* S = (uint32_t*)c->ntt_b.get((2 * nchunks + 2) * P::N * 4);
+    uint32_t* H = S + (nchunks + 1) * P::N;
+    uint64_t blocks = (nchunks + 255) / 256, cap = (uint64_t)c->sm_count * 8;
+    const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    ZKM_LAUNCH(k_quot_chunk_sums<P>, grid, 256, 0, s, (const uint32_t*)d_coeffs, (uint64_t)n, (const uint32_t*)d_point, S, nchunks);
+    ZKM_LAUNCH(k_quot_boundaries<P>, 1, ZKM_QUOT_T, ZKM_QUOT_T * P::N * 4, s, (const uint32_t*)S, nchunks, per,
+               (const uint32_t*)d_point, H);
+    ZKM_LAUNCH(k_quot_fill<P>, grid, 256, 0, s, (const uint32_t*)d_coeffs, (uint64_t)n, (const uint32_t*)d_point,
+               (const uint32_t*)H, (uint32_t*)d_quot, nchunks);
+    if (d_eval) ZKM_CUDA(cudaMemcpyAsync(d_eval, H, P::N * 4, cudaMemcpyDeviceToDevice, s));
+}
+
 // ---------------------------------------------------------------------------------- host side
 enum TableKind : uint64_t { TW = 1, COSET_LO = 2, COSET_HI = 3, DOMAIN = 4, VANISH = 5 };
 static uint64_t table_key(uint64_t kind, int curve, int k, int inverse) {
@@ -409,19 +517,20 @@ static void get_coset(Context* c, int curve, int k, int inverse, cudaStream_t s,
 template <class P, int R>
 static void launch_pass(Context* c, const NttPassArgs& a, cudaStream_t s) {
     typedef NttCfg<R, P::N> C;
-    static bool attr_set = false;
-    if (!attr_set && C::SMEM > 48 * 1024) {
-        ZKM_CUDA(cudaFuncSetAttribute(k_ntt_pass<P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
+    // Function attributes and occupancy are per device (one process may drive several GPUs) and this runs from
+    // concurrent lanes: per-ordinal atomics, the CUDA calls themselves are idempotent.
+    static std::atomic<int> per_sm_dev[64];
+    const int ord = c->device & 63;
+    int per_sm = per_sm_dev[ord].load(std::memory_order_acquire);
+    if (per_sm == 0) {
+        if (C::SMEM > 48 * 1024)
+            ZKM_CUDA(cudaFuncSetAttribute(k_ntt_pass<P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        ZKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ntt_pass<P, R>, C::NT, C::SMEM));
+        if (per_sm < 1) per_sm = 1;
+        per_sm_dev[ord].store(per_sm, std::memory_order_release);
     }
     uint64_t num_tiles = 1ull << (a.k - R);
     uint64_t ctas = (num_tiles + C::TILES - 1) / C::TILES;
-    // persistent grid: a multiple of the SM count, exactly as many CTAs per SM as are co-resident
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        ZKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ntt_pass<P, R>, C::NT, C::SMEM));
-        if (per_sm < 1) per_sm = 1;
-    }
     uint64_t cap = (uint64_t)c->sm_count * per_sm;
     unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
     ZKM_LAUNCH((k_ntt_pass<P, R>), grid, C::NT, C::SMEM, s, a);

@@ -12,6 +12,15 @@ void ntt_run_bw6(Context* c, const uint64_t* d_in, uint64_t* d_out, uint32_t log
 void ntt_domain_constants_bw6(Context* c, uint32_t* d, int log_n);
 void witness_map_bw6(Context* c, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h, cudaStream_t s);
 void fr_into_repr_bw6(Context* c, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t s);
+void kzg_quotient_bn(Context* c, const uint64_t* d_coeffs, size_t n, const uint64_t* d_point, uint64_t* d_quot, uint64_t* d_eval, cudaStream_t s);
+void kzg_quotient_bw6(Context* c, const uint64_t* d_coeffs, size_t n, const uint64_t* d_point, uint64_t* d_quot, uint64_t* d_eval, cudaStream_t s);
+void kzg_quotient_run(Context* c, int curve, const uint64_t* d_coeffs, size_t n, const uint64_t* d_point, uint64_t* d_quot,
+                      uint64_t* d_eval, cudaStream_t s) {
+    if (curve == ZKM_CURVE_BLS12_381) kzg_quotient_t<Bls12_381_FrP>(c, d_coeffs, n, d_point, d_quot, d_eval, s);
+    else if (curve == ZKM_CURVE_BN254) kzg_quotient_bn(c, d_coeffs, n, d_point, d_quot, d_eval, s);
+    else if (curve == ZKM_CURVE_BW6_761) kzg_quotient_bw6(c, d_coeffs, n, d_point, d_quot, d_eval, s);
+    else ZKM_FAIL(ZKM_ERR_ARG, "unknown curve id %d", curve);
+}
 void fr_into_repr_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t s) {
     if (curve == ZKM_CURVE_BLS12_381) fr_into_repr_t<Bls12_381_FrP>(c, d_in, d_out, n, s);
     else if (curve == ZKM_CURVE_BN254) fr_into_repr_bn(c, d_in, d_out, n, s);

@@ -15,5 +15,9 @@ void fr_into_repr_bn(Context* c, const uint64_t* d_in, uint64_t* d_out, uint64_t
 void ntt_domain_constants_bn(Context* c, uint32_t* d, int log_n) {
     ZKM_LAUNCH(k_domain_constants<Bn254_FrP>, 1, 32, 0, c->stream, d, log_n);
 }
+void kzg_quotient_bn(Context* c, const uint64_t* d_coeffs, size_t n, const uint64_t* d_point, uint64_t* d_quot, uint64_t* d_eval,
+                     cudaStream_t s) {
+    kzg_quotient_t<Bn254_FrP>(c, d_coeffs, n, d_point, d_quot, d_eval, s);
+}
 
 }  // namespace zkm

@@ -45,20 +45,20 @@ def witness_map(a, b, c, curve="bls12_381") -> np.ndarray:
 class ProvingKeyMSMs:
     """The five MSM bases of a Groth16 proving key, resident in HBM."""
 
-    def __init__(self, curve, h_query, l_query, a_query, b_g1_query, b_g2_query, infinity=None, precompute=True):
+    def __init__(self, curve, h_query, l_query, a_query, b_g1_query, b_g2_query, infinity=None, precompute=True,
+                 g2_device: int | None = None):
+        """g2_device: index of the initialised GPU that holds the b_g2 query (the G2 MSM runs on its own GPU
+        next to the G1 ones); default: device 1 when the process initialised more than one GPU, else the primary."""
         cid = _curve_id(curve)
         infinity = infinity or {}
-        if precompute:
-            _lib.set_option("msm_precompute", 1)
-        try:
-            self.h = RegisteredBases(cid, 1, h_query, infinity.get("h"))
-            self.l = RegisteredBases(cid, 1, l_query, infinity.get("l"))
-            self.a = RegisteredBases(cid, 1, a_query, infinity.get("a"))
-            self.b_g1 = RegisteredBases(cid, 1, b_g1_query, infinity.get("b_g1"))
-            self.b_g2 = RegisteredBases(cid, 2, b_g2_query, infinity.get("b_g2"))
-        finally:
-            if precompute:
-                _lib.set_option("msm_precompute", 0)
+        if g2_device is None and _lib.initialised_devices() > 1:
+            g2_device = 1
+        kw = {"precompute": bool(precompute)}
+        self.h = RegisteredBases(cid, 1, h_query, infinity.get("h"), **kw)
+        self.l = RegisteredBases(cid, 1, l_query, infinity.get("l"), **kw)
+        self.a = RegisteredBases(cid, 1, a_query, infinity.get("a"), **kw)
+        self.b_g1 = RegisteredBases(cid, 1, b_g1_query, infinity.get("b_g1"), **kw)
+        self.b_g2 = RegisteredBases(cid, 2, b_g2_query, infinity.get("b_g2"), device=g2_device, **kw)
 
     def prove_msms(self, h_scalars, aux_scalars, full_scalars) -> dict:
         """h_acc, l_acc and the MSM parts of g_a, g1_b, g2_b (calculate_coeff's `acc`).  Upstream runs the

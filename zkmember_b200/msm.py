@@ -68,16 +68,22 @@ class RegisteredBases:
     """Bases uploaded once to HBM (a proving-key query vector or the KZG powers), used by handle.
     The proving key is static across proofs (/root/reference/benches/groth16.rs:107-115)."""
 
-    def __init__(self, curve, group: int, bases, infinity=None, *, _device_ptr=None, _n=None):
+    def __init__(self, curve, group: int, bases, infinity=None, *, precompute: bool = False, shard: bool = False,
+                 device: int | None = None, _device_ptr=None, _n=None):
+        """precompute: also store the window multiples (ZKM_REG_PRECOMPUTE); shard: split the bases over all
+        initialised GPUs (ZKM_REG_SHARD); device: index of the initialised GPU that holds them (ZKM_REG_DEVICE)."""
         self.curve = _curve_id(curve)
         self.group = int(group)
         L = _lib.lib()
         W = coord_words(self.curve, self.group)
         h = ctypes.c_uint64(0)
+        flags = (_lib.REG_PRECOMPUTE if precompute else 0) | (_lib.REG_SHARD if shard else 0)
+        if device is not None:
+            flags |= _lib.REG_DEVICE(device)
         if _device_ptr is not None:
             self.n = int(_n)
-            _lib.check(L.zkm_bases_register_device(self.curve, self.group, ctypes.c_void_p(_device_ptr),
-                                                   ctypes.c_void_p(0), self.n, ctypes.byref(h)))
+            _lib.check(L.zkm_bases_register_ex(self.curve, self.group, ctypes.c_void_p(_device_ptr),
+                                               ctypes.c_void_p(0), self.n, flags, ctypes.byref(h)))
         else:
             b = _as_u64(bases, 2 * W, "bases")
             self.n = len(b)
@@ -86,12 +92,12 @@ class RegisteredBases:
                 inf = np.ascontiguousarray(infinity, dtype=np.uint8)
                 if len(inf) != self.n:
                     raise ValueError("infinity flags: expected %d, got %d" % (self.n, len(inf)))
-            _lib.check(L.zkm_bases_register(self.curve, self.group, _ptr(b), _ptr(inf), self.n, ctypes.byref(h)))
+            _lib.check(L.zkm_bases_register_ex(self.curve, self.group, _ptr(b), _ptr(inf), self.n, flags, ctypes.byref(h)))
         self.handle = h.value
 
     @classmethod
-    def from_device(cls, curve, group: int, device_ptr: int, n: int) -> "RegisteredBases":
-        return cls(curve, group, None, _device_ptr=device_ptr, _n=n)
+    def from_device(cls, curve, group: int, device_ptr: int, n: int, **kw) -> "RegisteredBases":
+        return cls(curve, group, None, _device_ptr=device_ptr, _n=n, **kw)
 
     def release(self):
         if self.handle:
