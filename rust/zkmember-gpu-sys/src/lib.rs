@@ -8,10 +8,22 @@ pub const ZKM_CURVE_BLS12_381: i32 = 0;
 pub const ZKM_CURVE_BN254: i32 = 1;
 pub const ZKM_CURVE_BW6_761: i32 = 2; // 12-word coordinates (G1 and G2 both over Fq), 6-word scalars / Fr elements
 pub const ZKM_OK: i32 = 0;
+pub const ZKM_REG_PRECOMPUTE: u32 = 1;
+pub const ZKM_REG_SHARD: u32 = 2;
+pub const fn zkm_reg_device(i: u32) -> u32 { (i + 1) << 8 }
 pub const ZKM_ERR_DOMAIN: i32 = -4;
 
 extern "C" {
     pub fn zkm_init(device: i32) -> i32;
+    pub fn zkm_init_mask(device_mask: u32) -> i32;
+    pub fn zkm_bases_register_ex(curve: i32, group: i32, bases_xy: *const u64, infinity: *const u8, n: usize, flags: u32,
+                                 handle_out: *mut u64) -> i32;
+    pub fn zkm_kzg_commit_batch(handle: u64, count: i32, coeffs: *const *const u64, n: *const usize, out_xy: *mut u64,
+                                out_inf: *mut u8) -> i32;
+    pub fn zkm_kzg_commit_hiding(handle_g: u64, handle_gamma_g: u64, coeffs: *const u64, n: usize, blinding: *const u64,
+                                 nb: usize, out_xy: *mut u64, out_inf: *mut u8) -> i32;
+    pub fn zkm_kzg_open(handle_g: u64, handle_gamma_g: u64, coeffs: *const u64, n: usize, blinding: *const u64, nb: usize,
+                        point: *const u64, out_w_xy: *mut u64, out_w_inf: *mut u8, out_random_v: *mut u64) -> i32;
     pub fn zkm_shutdown();
     pub fn zkm_last_error() -> *const c_char;
     pub fn zkm_device_count() -> i32;
@@ -44,12 +56,17 @@ pub fn check(rc: i32, what: &str) {
     }
 }
 
-/// One-time process initialisation (device from ZKM_DEVICE, default 0).
+/// One-time process initialisation: `ZKM_DEVICE_MASK` (bit i = CUDA device i; one process driving several GPUs, the
+/// G2 query / sharded registrations use the others) or `ZKM_DEVICE` (one GPU, default 0).
 pub fn ensure_init() {
     use std::sync::Once;
     static INIT: Once = Once::new();
     INIT.call_once(|| {
-        let dev = std::env::var("ZKM_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
-        check(unsafe { zkm_init(dev) }, "zkm_init");
+        if let Some(mask) = std::env::var("ZKM_DEVICE_MASK").ok().and_then(|s| u32::from_str_radix(s.trim_start_matches("0x"), 16).ok()) {
+            check(unsafe { zkm_init_mask(mask) }, "zkm_init_mask");
+        } else {
+            let dev = std::env::var("ZKM_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
+            check(unsafe { zkm_init(dev) }, "zkm_init");
+        }
     });
 }

@@ -286,7 +286,11 @@ static void msm_reg_host(const std::shared_ptr<BasesReg>& reg, size_t offset, co
     LaneGuard home(0);
     ZKM_CUDA(cudaSetDevice(home.c->device));
     StreamScope hscope(home.c, home.c->stream);
-    char* d_gather = (char*)home.c->gather.get(jobs.size() * rb + rb);
+    // k_msm_final / k_points_sum WRITE records with 128-bit stores (16-byte aligned destinations only); records are 8 n + 8
+    // bytes long, so only the first slot of a packed array is aligned: the sum goes to offset 0, the gathered records
+    // (which are only ever written by copies and read limb by limb) follow from offset `gofs`
+    const size_t gofs = (rb + 15) & ~(size_t)15;
+    char* d_gather = (char*)home.c->gather.get(gofs + jobs.size() * rb);
     const int home_ord = home.c->device;
     std::vector<int32_t> rc(jobs.size(), ZKM_OK);
     std::vector<std::string> msg(jobs.size());
@@ -300,7 +304,7 @@ static void msm_reg_host(const std::shared_ptr<BasesReg>& reg, size_t offset, co
                 StreamScope scope(c, c->stream);
                 uint64_t* d_rec = (uint64_t*)c->io_out.get(rb);
                 one(c, jobs[i], d_rec);
-                ZKM_CUDA(cudaMemcpyPeerAsync(d_gather + i * rb, home_ord, d_rec, c->device, rb, c->stream));
+                ZKM_CUDA(cudaMemcpyPeerAsync(d_gather + gofs + i * rb, home_ord, d_rec, c->device, rb, c->stream));
                 ZKM_CUDA(cudaStreamSynchronize(c->stream));
             });
             if (rc[i] != ZKM_OK) msg[i] = t_err;
@@ -313,8 +317,8 @@ static void msm_reg_host(const std::shared_ptr<BasesReg>& reg, size_t offset, co
             throw ZkmError{rc[i]};
         }
     ZKM_CUDA(cudaSetDevice(home.c->device));
-    uint64_t* d_sum = (uint64_t*)(d_gather + jobs.size() * rb);
-    points_sum_run(home.c, r.curve, r.group, (const uint64_t*)d_gather, jobs.size(), d_sum, home.c->stream);
+    uint64_t* d_sum = (uint64_t*)d_gather;
+    points_sum_run(home.c, r.curve, r.group, (const uint64_t*)(d_gather + gofs), jobs.size(), d_sum, home.c->stream);
     read_back(home.c, d_sum);
 }
 
@@ -348,15 +352,18 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
     ZKM_CUDA(cudaSetDevice(hc->device));
     cudaStream_t caller = caller_or_null ? caller_or_null : hc->stream;
     StreamScope hscope(hc, caller);
-    struct Flat { size_t item, slot; Job job; };
+    struct Flat { size_t item, k; Job job; };
     std::vector<Flat> flat;
-    std::vector<size_t> first_slot(items.size()), njobs(items.size());
-    size_t slots = 0;
+    std::vector<size_t> njobs(items.size()), goff(items.size(), 0);
+    size_t gbytes = 0;       // sharded items gather their partial records at goff[item] + k * rec_bytes (copies only)
     for (size_t i = 0; i < items.size(); i++) {
         std::vector<Job> jobs = split_jobs(*items[i].reg, items[i].offset, items[i].n);
-        first_slot[i] = slots;
         njobs[i] = jobs.size();
-        for (Job& j : jobs) flat.push_back(Flat{i, slots++, j});
+        for (size_t k = 0; k < jobs.size(); k++) flat.push_back(Flat{i, k, jobs[k]});
+        if (jobs.size() > 1) {
+            goff[i] = gbytes;
+            gbytes += (jobs.size() * rec_bytes(items[i].reg->curve, items[i].reg->group) + 15) & ~(size_t)15;
+        }
     }
     // fast path: one job on the caller's device -> no threads, no events, the caller's stream itself
     if (items.size() == 1 && flat.size() == 1 && flat[0].job.part->dev == home) {
@@ -372,9 +379,7 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
             msm_run(hc, r.curve, r.group, nullptr, nullptr, nullptr, 0, items[i].d_out, caller);   // identity
         }
     if (flat.empty()) return;
-    size_t max_rb = 0;
-    for (auto& it : items) max_rb = std::max(max_rb, rec_bytes(it.reg->curve, it.reg->group));
-    char* d_gather = (char*)hc->gather.get((slots + 1) * max_rb);
+    char* d_gather = (char*)hc->gather.get(gbytes + 16);
     cudaEvent_t ev_in;
     ZKM_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     ZKM_CUDA(cudaEventRecord(ev_in, caller));
@@ -403,9 +408,11 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
                     ZKM_CUDA(cudaMemcpyPeerAsync(local, c->device, d_scal, home_ord, fj.job.count * sbytes, s));
                     d_scal = local;
                 }
-                // single-job items write their record straight to the caller's buffer, sharded ones to a gather slot
-                uint64_t* dst = njobs[fj.item] == 1 ? it.d_out : (uint64_t*)(d_gather + fj.slot * max_rb);
-                if (remote) {
+                // single-job items on the caller's device write their record straight to the caller's buffer (16-byte
+                // aligned by contract); everything else goes through the lane's own aligned record and a copy
+                const bool sharded = njobs[fj.item] > 1;
+                uint64_t* dst = sharded ? (uint64_t*)(d_gather + goff[fj.item] + fj.k * rb) : it.d_out;
+                if (remote || sharded) {
                     uint64_t* d_rec = (uint64_t*)c->io_out.get(rb);
                     run_part(c, r, fj.job, d_scal, d_rec, s);
                     ZKM_CUDA(cudaMemcpyPeerAsync(dst, home_ord, d_rec, c->device, rb, s));
@@ -436,13 +443,7 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
     for (size_t i = 0; i < items.size(); i++)
         if (njobs[i] > 1) {
             const BasesReg& r = *items[i].reg;
-            const size_t rb = rec_bytes(r.curve, r.group);
-            // gather slots are max_rb apart: compact this item's records when its record is shorter
-            char* base = d_gather + first_slot[i] * max_rb;
-            if (rb != max_rb)
-                for (size_t k = 1; k < njobs[i]; k++)
-                    ZKM_CUDA(cudaMemcpyAsync(base + k * rb, base + k * max_rb, rb, cudaMemcpyDeviceToDevice, caller));
-            points_sum_run(hc, r.curve, r.group, (const uint64_t*)base, njobs[i], items[i].d_out, caller);
+            points_sum_run(hc, r.curve, r.group, (const uint64_t*)(d_gather + goff[i]), njobs[i], items[i].d_out, caller);
         }
 }
 
@@ -832,10 +833,11 @@ static void add_two_points(int curve, int group, const uint64_t* a_xy, uint8_t a
     h[W2] = a_inf ? 1 : 0;
     memcpy(h + W2 + 1, b_xy, W2 * 8);
     h[2 * W2 + 1] = b_inf ? 1 : 0;
-    uint64_t* d = (uint64_t*)c->gather.get(3 * rb);
-    h2d(d, h, 2 * rb, c->stream);
-    points_sum_run(c, curve, group, d, 2, d + 2 * (W2 + 1), c->stream);
-    ZKM_CUDA(cudaMemcpyAsync(h + 2 * (W2 + 1), d + 2 * (W2 + 1), rb, cudaMemcpyDeviceToHost, c->stream));
+    const size_t gofs = (rb + 15) & ~(size_t)15;        // the sum (written with 128-bit stores) sits at the aligned start
+    char* d = (char*)c->gather.get(gofs + 2 * rb);
+    h2d(d + gofs, h, 2 * rb, c->stream);
+    points_sum_run(c, curve, group, (const uint64_t*)(d + gofs), 2, (uint64_t*)d, c->stream);
+    ZKM_CUDA(cudaMemcpyAsync(h + 2 * (W2 + 1), d, rb, cudaMemcpyDeviceToHost, c->stream));
     ZKM_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(out_xy, h + 2 * (W2 + 1), W2 * 8);
     *out_inf = h[2 * (W2 + 1) + W2] ? 1 : 0;
