@@ -30,6 +30,7 @@ namespace zkm {
     struct Tag {                                                                    \
         static constexpr int N = NLIMBS;                                            \
         static constexpr uint32_t INV = PREFIX##_INV32;                             \
+        static ZKM_DEV uint32_t inv_rt() { return PREFIX##_INVC[0]; }  /* INV as a run-time value (see gen_constants.py) */ \
         static constexpr int BITS = PREFIX##_BITS;                                  \
         static constexpr int UR = PREFIX##_UR;   /* radix bits of the carry-free product */ \
         static ZKM_CEXPR uint32_t modu(int i) { constexpr uint32_t t[] = PREFIX##_MODU; return t[i]; } \
@@ -157,6 +158,10 @@ template <class P>
 ZKM_DEV Fp<P> fp_mul_cios(const Fp<P>& a, const Fp<P>& b) {
     constexpr int N = P::N;
     static_assert((N & 1) == 0, "even limb count required");
+    // The reduction factor is formed with INV read from constant memory (P::inv_rt()), not the immediate: for the
+    // fields with p = 1 mod 2^32 (INV = 0xffffffff: BLS12-381 Fr, BW6-761 Fr) ptxas otherwise rewrites m = -t and then
+    // leaves every m * p_i pair unfused (IMAD.X + IMAD.HI.U32.X, 6 issue cycles instead of the 4 of one
+    // IMAD.WIDE.U32.X): 280 instead of 228 instructions per 8-limb product (SASS: profiles/int_pipe_peak_r2.sass.txt).
     uint32_t acc[2][2 * N + 2];
     ZKM_UNROLL
     for (int i = 0; i < 2 * N + 2; i++) {
@@ -197,7 +202,7 @@ ZKM_DEV Fp<P> fp_mul_cios(const Fp<P>& a, const Fp<P>& b) {
             }
             X[j + N] = ptx::addc(X[j + N], 0);
         }
-        const uint32_t m = ptx::mul_lo(X[j], P::INV);
+        const uint32_t m = ptx::mul_lo(X[j], P::inv_rt());
         Y[j + 1] = ptx::mad_lo_cc(m, P::mod(1), Y[j + 1]);
         Y[j + 2] = ptx::madc_hi_cc(m, P::mod(1), Y[j + 2]);
         ZKM_UNROLL

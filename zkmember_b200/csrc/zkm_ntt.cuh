@@ -185,8 +185,15 @@ __device__ __forceinline__ void ntt_round(Fp<P> (&x)[8], uint32_t tau, int pl, i
                 const uint32_t q = (((uint32_t)i >> rot) | ((uint32_t)i << (3 - rot))) & 7u;
                 const uint32_t slot = ntt_slot(tau, q, pl);
                 const uint32_t j = slot & ((1u << g) - 1u);
-                Fp<P> w = ld_fp<P>(tw_tile + ((size_t)j << t) * P::N);
-                x[i + 4] = fp_mul(d, w);
+                if (j == 0) {
+                    // w^0 as well.  In the last round of a pass (pl == 0) j depends on q only, so the branch is uniform
+                    // over the CTA and 3 of its 8 remaining products disappear; elsewhere the few lanes with j == 0
+                    // just sit out the product.
+                    x[i + 4] = d;
+                } else {
+                    Fp<P> w = ld_fp<P>(tw_tile + ((size_t)j << t) * P::N);
+                    x[i + 4] = fp_mul(d, w);
+                }
             }
         }
         ntt_rotate<P>(x);
