@@ -157,10 +157,14 @@ __device__ __forceinline__ void dbl_sel(XYZZ<F>& p) {
 
 // Thread (w, t) owns buckets b in [t*g, (t+1)*g) of window w:  sum_b (b+1) S_b = acc + lo * run with
 // run = sum S_b, acc = sum (b - lo + 1) S_b (running sums from the top), lo = t*g.
-template <class F>
+// HIER: store `run` next to `acc` instead of adding lo * run here.  The offsets lo = t * g are then applied by running
+// the SAME reduction over the run sums one level up (sum_t t * run_t, see OpsImpl::reduce): no per-thread scalar
+// multiplication -- 19 doublings + ~10 additions per thread at c = 20, 17 % on top of the 2 g additions of the loop
+// (55 % at the g = 16 of a 2^21-point shard).
+template <class F, bool HIER>
 __global__ void __launch_bounds__(128)   // (128, 3) was measured: the register cap spills, 15.8 -> 18.1 ms at 2^24
 k_bucket_reduce(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
-                uint32_t W, uint32_t B, uint32_t g, XYZZ<F>* __restrict__ contrib) {
+                uint32_t W, uint32_t B, uint32_t g, XYZZ<F>* __restrict__ contrib, XYZZ<F>* __restrict__ run_out) {
     const uint32_t per_w = B / g;
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= W * per_w) return;
@@ -203,7 +207,9 @@ k_bucket_reduce(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ 
             xyzz_add_ni(acc, run);
         }
     }
-    if (lo != 0 && !run.is_identity()) {
+    if (HIER) {
+        st_xyzz(run_out + gid, run);
+    } else if (lo != 0 && !run.is_identity()) {
         XYZZ<F> r = XYZZ<F>::identity();
         for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
             xyzz_dbl_ni(r);
@@ -212,6 +218,53 @@ k_bucket_reduce(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ 
         xyzz_add_ni(acc, r);
     }
     st_xyzz(contrib + gid, acc);
+}
+
+// Upper levels of the hierarchical reduction: the same running sums over a DENSE array of XYZZ points (the run sums
+// of the level below, bucket b = in[w * stride_w + first + b], b < Bp), four lanes per chain (little work, all
+// latency).  acc_out[w * per2 + t] = sum_{b in chunk t} (b - t g + 1) S_b,  run_out[...] = sum_{b in chunk t} S_b.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_dense_quad(const XYZZ<F>* __restrict__ in, uint32_t stride_w, uint32_t first, uint32_t Bp, uint32_t g, uint32_t per2,
+                    uint32_t W, XYZZ<F>* __restrict__ acc_out, XYZZ<F>* __restrict__ run_out) {
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (gid >= W * per2) return;
+    const int q = threadIdx.x & 3;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    const uint32_t w = gid / per2, t = gid % per2;
+    const uint32_t lo = t * g, hi = lo + g < Bp ? lo + g : Bp;
+    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+    for (uint32_t b = hi; b-- > lo;) {
+        XYZZ<F> S = ld_xyzz(in + (size_t)w * stride_w + first + b);
+        xyzz_add_quad(run, S, q, mask);
+        xyzz_add_quad(acc, run, q, mask);
+    }
+    if (q == 0) {
+        st_xyzz(acc_out + gid, acc);
+        st_xyzz(run_out + gid, run);
+    }
+}
+
+// window total = A_0 + G_0 (A_1 + G_1 (A_2 + ...)) with A_k = sums[k * W + w] (the plain sums of the levels' acc
+// arrays) and G_k = 2^lg[k] the chunk length of level k: log2(B) doublings per window in all.  One quad per window.
+struct ReduceLevels {
+    int n;
+    int lg[8];
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_window_combine(const XYZZ<F>* __restrict__ sums, ReduceLevels lv, uint32_t W,
+                                                        XYZZ<F>* __restrict__ wsum) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (w >= W) return;
+    const int q = threadIdx.x & 3;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    XYZZ<F> v = ld_xyzz(sums + (size_t)(lv.n - 1) * W + w);
+    for (int k = lv.n - 2; k >= 0; k--) {
+        for (int i = 0; i < lv.lg[k]; i++) xyzz_dbl_quad(v, q, mask);
+        XYZZ<F> a = ld_xyzz(sums + (size_t)k * W + w);
+        xyzz_add_quad(v, a, q, mask);
+    }
+    if (q == 0) st_xyzz(wsum + w, v);
 }
 
 // out[w * nslices + slice] = sum of in[w * per_w + slice * chunk ... + chunk)   (block = 64 threads)
@@ -528,18 +581,50 @@ struct OpsImpl {
                 ZKM_LAUNCH(k_window_sum_quad<F>, RW, 128, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u, (XYZZ<F>*)wsum);
             }
         } else {
+            // Hierarchical running sums.  Level 0: one thread per chunk of g buckets -> acc (weights relative to the
+            // chunk) and run (plain chunk sum).  The chunk offsets t * g are worth g * sum_t t * run_t: the same
+            // reduction over the run sums (a dense array now, four lanes per chain), and so on until one chunk is left.
+            XYZZ<F>* acc0 = (XYZZ<F>*)contrib;                       // RW * per_w
+            XYZZ<F>* stage2 = acc0 + (size_t)RW * per_w;             // slice sums of the level-0 window sum
+            XYZZ<F>* run0 = stage2 + (size_t)RW * ((per_w + 1023) / 1024) + 1;
+            XYZZ<F>* upper = run0 + (size_t)RW * per_w;              // acc / run of the upper levels
             unsigned rblocks = (RW * per_w + 127) / 128;
-            ZKM_LAUNCH(k_bucket_reduce<F>, rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, RW, pl.B, g,
-                       (XYZZ<F>*)contrib);
-            // two-step sum of the per-slice contributions of every window: per_w -> nslices -> 1
-            uint32_t nslices = (per_w + 1023) / 1024;
-            if (nslices > 1) {
-                uint32_t chunk = (per_w + nslices - 1) / nslices;
-                ZKM_LAUNCH(k_window_sum<F>, RW * nslices, 64, 0, s, (const XYZZ<F>*)contrib, per_w, chunk, nslices, stage);
-                ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)stage, nslices, nslices, 1u, (XYZZ<F>*)wsum);
-            } else {
-                ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)contrib, per_w, per_w, 1u, (XYZZ<F>*)wsum);
+            ZKM_LAUNCH((k_bucket_reduce<F, true>), rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, RW, pl.B, g, acc0, run0);
+            ReduceLevels lv;
+            lv.n = 1;
+            lv.lg[0] = 31 - __builtin_clz(g);
+            size_t used = 0;                                           // records of `upper` in use
+            auto take = [&](size_t n) { XYZZ<F>* p = upper + used; used += n; return p; };
+            XYZZ<F>* sums = take((size_t)8 * RW);
+            // plain sum of the level-0 acc array: two-step tree per window
+            {
+                uint32_t nslices = (per_w + 1023) / 1024;
+                if (nslices > 1) {
+                    uint32_t chunk = (per_w + nslices - 1) / nslices;
+                    ZKM_LAUNCH(k_window_sum<F>, RW * nslices, 64, 0, s, (const XYZZ<F>*)acc0, per_w, chunk, nslices, stage2);
+                    ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)stage2, nslices, nslices, 1u, sums);
+                } else {
+                    ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)acc0, per_w, per_w, 1u, sums);
+                }
             }
+            const XYZZ<F>* cur_run = run0;
+            uint32_t cur_per = per_w;
+            while (cur_per > 1) {
+                const uint32_t Bp = cur_per - 1;                      // chunk t >= 1 has weight t: bucket b = t - 1
+                uint32_t gk = 8;
+                if (Bp <= 32) { gk = 1; while (gk < Bp) gk <<= 1; }   // last level: one chunk
+                const uint32_t per2 = (Bp + gk - 1) / gk;
+                XYZZ<F>* acck = take((size_t)RW * per2);
+                XYZZ<F>* runk = take((size_t)RW * per2);
+                ZKM_LAUNCH(k_reduce_dense_quad<F>, (RW * per2 * 4 + 127) / 128, 128, 0, s, cur_run, cur_per, 1u, Bp, gk, per2, RW,
+                           acck, runk);
+                ZKM_LAUNCH(k_window_sum_quad<F>, RW, 128, 0, s, (const XYZZ<F>*)acck, per2, per2, 1u, sums + (size_t)lv.n * RW);
+                lv.lg[lv.n] = 31 - __builtin_clz(gk);
+                lv.n++;
+                cur_run = runk;
+                cur_per = per2;
+            }
+            ZKM_LAUNCH(k_window_combine<F>, (RW * 4 + 127) / 128, 128, 0, s, (const XYZZ<F>*)sums, lv, RW, (XYZZ<F>*)wsum);
         }
         ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.RW, pl.c, d_out);
     }

@@ -80,6 +80,18 @@ __global__ void k_gen_twiddles(uint32_t* out, int k, int inverse, uint64_t count
     st_fp<P>(out + e * P::N, r);
 }
 
+// four-step twiddles of a non-final pass in TILE order: out[(lo << R) + j] = w_kk^(lo * bitrev_R(j)), lo < 2^(kk - R)
+template <class P>
+__global__ void k_gen_tw4(uint32_t* out, int kk, int R, int inverse) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (1ull << kk)) return;
+    const uint64_t lo = idx >> R;
+    const uint32_t j = (uint32_t)(idx & ((1u << R) - 1u));
+    const uint32_t u = __brev(j) >> (32 - R);
+    Fp<P> w = group_gen<P>(kk, inverse != 0);
+    st_fp<P>(out + idx * P::N, fp_pow_u64(w, lo * (uint64_t)u));
+}
+
 // coset tables: lo[j] = c * g^(+-j), j < nlo ; hi[j] = g^(+-j*nlo), j < nhi ; c = 1 (forward) or n^-1 (inverse)
 template <class P>
 __global__ void k_gen_coset(uint32_t* lo, uint32_t* hi, uint64_t nlo, uint64_t nhi, int inverse, int k) {
@@ -116,7 +128,9 @@ struct NttPassArgs {
     const uint32_t* in;
     uint32_t* out;
     const uint32_t* tw_tile;   // w_{2^R}^e, e < 2^(R-1)
-    const uint32_t* tw_four;   // w_{n'}^e, e < n'/2 (non-final passes)
+    const uint32_t* tw_four;   // w_{n'}^e, e < n'/2 (non-final passes; fallback when the per-tile table would be too large)
+    const uint32_t* tw_four_tile;  // w_{n'}^(lo * bitrev_R(j)) laid out [lo][j]: what tile `lo` multiplies its slot j by,
+                               // in the order its threads hold the slots -> one coalesced 2^R-element read per tile
     const uint32_t* coset_lo;  // fused coset / size_inv scaling (first or last pass), may be null
     const uint32_t* coset_hi;
     const uint32_t* size_inv;  // n^-1 (non-coset inverse, last pass)
@@ -280,13 +294,18 @@ __global__ void __launch_bounds__((NttCfg<R, P::N>::NT), (NttCfg<R, P::N>::MINB)
                 const uint32_t u = __brev(j) >> (32 - R);
                 if (!a.last) {
                     // four-step twiddle w_{n'}^(lo * u), then in place at the bit-reversed slot
-                    uint64_t e = lo_idx * (uint64_t)u;
-                    const uint64_t half = 1ull << (kk - 1);
-                    bool negate = e >= half;
-                    if (negate) e -= half;
-                    Fp<P> w = ld_fp<P>(a.tw_four + e * P::N);
-                    Fp<P> v = fp_mul(x[q], w);
-                    if (negate) v = fp_neg(v);
+                    Fp<P> v;
+                    if (a.tw_four_tile) {
+                        v = fp_mul(x[q], ld_fp<P>(a.tw_four_tile + ((lo_idx << R) + j) * P::N));
+                    } else {
+                        uint64_t e = lo_idx * (uint64_t)u;
+                        const uint64_t half = 1ull << (kk - 1);
+                        bool negate = e >= half;
+                        if (negate) e -= half;
+                        Fp<P> w = ld_fp<P>(a.tw_four + e * P::N);
+                        v = fp_mul(x[q], w);
+                        if (negate) v = fp_neg(v);
+                    }
                     st_fp<P>(a.out + (gbase + ((uint64_t)j << logL)) * P::N, v);
                 } else {
                     // natural-order position: u * 2^(k-R) + bitrev_{k-R}(hi)
@@ -473,7 +492,7 @@ static void kzg_quotient_t(Context* c, const uint64_t* d_coeffs, size_t n, const
 }
 
 // ---------------------------------------------------------------------------------- host side
-enum TableKind : uint64_t { TW = 1, COSET_LO = 2, COSET_HI = 3, DOMAIN = 4, VANISH = 5 };
+enum TableKind : uint64_t { TW = 1, COSET_LO = 2, COSET_HI = 3, DOMAIN = 4, VANISH = 5, TW4 = 6 };
 static uint64_t table_key(uint64_t kind, int curve, int k, int inverse) {
     return (kind << 32) | ((uint64_t)curve << 16) | ((uint64_t)inverse << 8) | (uint64_t)k;
 }
@@ -492,6 +511,26 @@ static const uint32_t* get_twiddles(Context* c, int curve, int k, int inverse, c
     unsigned blocks = (unsigned)((count + 255) / 256);
     ZKM_LAUNCH(k_gen_twiddles<P>, blocks, 256, 0, s, (uint32_t*)p, k, inverse, count);
     ZKM_CUDA(cudaStreamSynchronize(s));  // first use only: other lanes' streams may read the table right away
+    return (const uint32_t*)p;
+}
+
+// Per-tile four-step table of a non-final pass (2^kk elements).  The gather table `tw_four` costs a random 32-byte
+// DRAM access per element (ncu r1: 1.84 GB read in pass 1 of a 2^24 transform for 0.54 GB of data); this layout is
+// read front to back.  Built once per (size, tile radix, direction); above ZKM_TW4_MAX_BYTES the gather table is used.
+constexpr size_t ZKM_TW4_MAX_BYTES = (size_t)512 << 20;
+template <class P>
+static const uint32_t* get_tw4(Context* c, int curve, int kk, int R, int inverse, cudaStream_t s) {
+    const size_t bytes = ((size_t)P::N * 4) << kk;
+    if (bytes > ZKM_TW4_MAX_BYTES) return nullptr;
+    std::lock_guard<std::mutex> tw_lock(c->sh->tw_mu);
+    const uint64_t key = table_key(TW4, curve, kk, inverse) | ((uint64_t)R << 40);
+    auto it = c->twiddles.find(key);
+    if (it != c->twiddles.end()) return (const uint32_t*)it->second;
+    void* p = nullptr;
+    ZKM_CUDA(cudaMalloc(&p, bytes));
+    c->twiddles[key] = p;
+    ZKM_LAUNCH(k_gen_tw4<P>, (unsigned)(((1ull << kk) + 255) / 256), 256, 0, s, (uint32_t*)p, kk, R, inverse);
+    ZKM_CUDA(cudaStreamSynchronize(s));
     return (const uint32_t*)p;
 }
 
@@ -635,7 +674,8 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
         a.in = a.first ? in : work;
         a.out = a.last ? final_dst : work;
         a.tw_tile = get_twiddles<P>(c, curve, R, inverse, s);
-        a.tw_four = a.last ? nullptr : get_twiddles<P>(c, curve, k - s0, inverse, s);
+        a.tw_four_tile = a.last ? nullptr : get_tw4<P>(c, curve, k - s0, R, inverse, s);
+        a.tw_four = (a.last || a.tw_four_tile) ? nullptr : get_twiddles<P>(c, curve, k - s0, inverse, s);
         a.coset_lo = clo;
         a.coset_hi = chi;
         a.coset_lo_bits = clo_bits;
