@@ -239,8 +239,11 @@ def main():
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # host-side barrier for the one-process-N-GPUs leg: an NCCL barrier would keep a spinning kernel on every waiting GPU
+        cpu_group = dist.new_group(backend="gloo")
 
     import zkmember_b200 as zkm
     from zkmember_b200 import _lib
@@ -542,6 +545,8 @@ def main():
         torch.cuda.synchronize()
         cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "90",
                "--inflight", "3", "--device", str(local_rank)]
+        if world > 1:
+            cmd += ["--host-wait", "2"]      # replicas share the host's cores: block instead of spinning on the read-back
         if rank == 0 and world == 1 and not args.skip_cpu:
             cmd.append("--cpu")
         try:
@@ -581,6 +586,9 @@ def main():
     # ZKM_REG_SHARD; per-device host threads, partial sums gathered over NVLink P2P and added on device 0).  Rank 0 only,
     # after the per-rank measurements; the other ranks wait at the barrier below with their GPUs idle.
     single = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)           # every rank has finished its own GPU work: the GPUs are idle from here on
     if world > 1 and rank == 0 and not args.skip_single_process:
         try:
             reg.release()
@@ -613,7 +621,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             single = {"error": repr(e)}
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:

@@ -95,7 +95,9 @@ const char* zkm_version(void);
  * pointer, n) and validated by a content fingerprint on every call: 1 = FNV-1a over 512 evenly spaced records (cheap;
  * assumes the vector is not partially rewritten in place between calls), 2 = over every byte, 0 = no cache (upload
  * every time).  A fingerprint mismatch re-uploads.  Least-recently-used entries are dropped above
- * "msm_cache_max_mb" (default 32768). */
+ * "msm_cache_max_mb" (default 32768).  A cached vector of at most 2^18 bases that comes back a second time is
+ * re-registered with its window multiples (ZKM_REG_PRECOMPUTE; option "msm_cache_precompute", default 1): from the third
+ * call on the small MSMs of a real proving key run without the final doubling chain. */
 int32_t zkm_msm_g1(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity,
                    const uint64_t* scalars, size_t n, uint64_t* out_xy, uint8_t* out_inf);
 int32_t zkm_msm_g2(int32_t curve, const uint64_t* bases_xy, const uint8_t* infinity,
@@ -215,7 +217,9 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
  * keys / SRS that are reused across many proofs), "msm_xarr" (0 | 1: level-0 x-coordinate array, default 1),
  * "msm_prefetch_fwd" / "msm_prefetch_bwd" (L2 prefetch distance of the level-0 gathers, default 0 = off),
  * "msm_cache" (0 | 1 | 2) and "msm_cache_max_mb" (registration cache of zkm_msm_g1/g2, see there),
- * "spread_host_calls" (0 | 1: host-pointer zkm_ntt / zkm_witness_map calls rotate over the initialised devices).
+ * "spread_host_calls" (0 | 1: host-pointer zkm_ntt / zkm_witness_map calls rotate over the initialised devices),
+ * "host_wait" (0 auto | 1 spin | 2 block: how an MSM waits for its one device read-back; 2 when several prover processes
+ * share the host's cores).
  * "msm_precompute" is the legacy form of ZKM_REG_PRECOMPUTE (a process-wide switch: prefer the flag).
  * Unknown keys fail with ZKM_ERR_ARG. */
 int32_t zkm_set_option(const char* key, int64_t value);

@@ -36,6 +36,8 @@ inline void check(int32_t rc, const char* what) {
     if (rc != ZKM_OK) throw Error(rc, std::string(what) + ": " + zkm_last_error());
 }
 inline void init(int device = 0) { check(zkm_init(device), "zkm_init"); }
+// one process, several GPUs (bit i = CUDA device i, lowest set bit = primary): see zkm_init_mask in zkm_b200.h
+inline void init_mask(uint32_t device_mask) { check(zkm_init_mask(device_mask), "zkm_init_mask"); }
 
 template <int L64>
 struct Fp {
@@ -244,8 +246,15 @@ inline std::vector<typename Curve::Fr> witness_map(const Radix2EvaluationDomain<
     return h;
 }
 
+// ark_poly_commit::kzg10 (0.3.0 src/kzg10/mod.rs): commit (with or without the hiding term), the commitments of one
+// prover round in one call, and open (witness polynomial on the device).  Blinding polynomials are the caller's.
+template <class Curve>
+struct KZGProof {              // kzg10::Proof { w, random_v }
+    G1Affine<Curve> w;
+    bool hiding;
+    typename Curve::Fr random_v;
+};
 struct KZG10 {
-    // non-hiding part of ark_poly_commit::kzg10::KZG10::commit
     template <class Curve>
     static G1Affine<Curve> commit(const RegisteredBases<Curve, 1>& powers_of_g, const std::vector<typename Curve::Fr>& coeffs) {
         std::vector<uint64_t> out(2 * sizeof(typename Curve::Fq) / 8);
@@ -253,6 +262,52 @@ struct KZG10 {
         check(zkm_kzg_commit(powers_of_g.handle(), reinterpret_cast<const uint64_t*>(coeffs.data()), coeffs.size(), out.data(), &out_inf),
               "zkm_kzg_commit");
         return detail::unpack<Curve, 1>(out, out_inf);
+    }
+    template <class Curve>
+    static G1Affine<Curve> commit(const RegisteredBases<Curve, 1>& powers_of_g, const RegisteredBases<Curve, 1>& powers_of_gamma_g,
+                                  const std::vector<typename Curve::Fr>& coeffs, const std::vector<typename Curve::Fr>& blinding) {
+        std::vector<uint64_t> out(2 * sizeof(typename Curve::Fq) / 8);
+        uint8_t out_inf = 0;
+        check(zkm_kzg_commit_hiding(powers_of_g.handle(), powers_of_gamma_g.handle(), reinterpret_cast<const uint64_t*>(coeffs.data()),
+                                    coeffs.size(), reinterpret_cast<const uint64_t*>(blinding.data()), blinding.size(), out.data(), &out_inf),
+              "zkm_kzg_commit_hiding");
+        return detail::unpack<Curve, 1>(out, out_inf);
+    }
+    template <class Curve>
+    static std::vector<G1Affine<Curve>> commit_batch(const RegisteredBases<Curve, 1>& powers_of_g,
+                                                     const std::vector<std::vector<typename Curve::Fr>>& polys) {
+        const size_t W2 = 2 * sizeof(typename Curve::Fq) / 8, k = polys.size();
+        std::vector<const uint64_t*> ptrs(k ? k : 1);
+        std::vector<size_t> ns(k ? k : 1);
+        for (size_t i = 0; i < k; i++) {
+            ptrs[i] = reinterpret_cast<const uint64_t*>(polys[i].data());
+            ns[i] = polys[i].size();
+        }
+        std::vector<uint64_t> out((k ? k : 1) * W2);
+        std::vector<uint8_t> inf(k ? k : 1);
+        check(zkm_kzg_commit_batch(powers_of_g.handle(), (int32_t)k, ptrs.data(), ns.data(), out.data(), inf.data()), "zkm_kzg_commit_batch");
+        std::vector<G1Affine<Curve>> res;
+        for (size_t i = 0; i < k; i++)
+            res.push_back(detail::unpack<Curve, 1>(std::vector<uint64_t>(out.begin() + i * W2, out.begin() + (i + 1) * W2), inf[i]));
+        return res;
+    }
+    // `powers_of_gamma_g` / `blinding` may be null / empty: non-hiding opening
+    template <class Curve>
+    static KZGProof<Curve> open(const RegisteredBases<Curve, 1>& powers_of_g, const std::vector<typename Curve::Fr>& coeffs,
+                                const typename Curve::Fr& point, const RegisteredBases<Curve, 1>* powers_of_gamma_g = nullptr,
+                                const std::vector<typename Curve::Fr>* blinding = nullptr) {
+        std::vector<uint64_t> out(2 * sizeof(typename Curve::Fq) / 8);
+        uint8_t out_inf = 0;
+        KZGProof<Curve> pr;
+        pr.hiding = powers_of_gamma_g && blinding && !blinding->empty();
+        std::memset(&pr.random_v, 0, sizeof(pr.random_v));
+        check(zkm_kzg_open(powers_of_g.handle(), pr.hiding ? powers_of_gamma_g->handle() : 0,
+                           reinterpret_cast<const uint64_t*>(coeffs.data()), coeffs.size(),
+                           pr.hiding ? reinterpret_cast<const uint64_t*>(blinding->data()) : nullptr, pr.hiding ? blinding->size() : 0,
+                           reinterpret_cast<const uint64_t*>(&point), out.data(), &out_inf, reinterpret_cast<uint64_t*>(&pr.random_v)),
+              "zkm_kzg_open");
+        pr.w = detail::unpack<Curve, 1>(out, out_inf);
+        return pr;
     }
 };
 

@@ -4,6 +4,8 @@
 //   msm <curve> <group> <n> <hex bases> <hex infinity flags> <hex scalars> <hex result> <result infinity>
 //   wmap <curve> <log_n> <hex a> <hex b> <hex c> <hex h>
 //   ser <curve> <group> <hex xy> <infinity> <hex compressed>     (host-only: checked BEFORE zkm::init, no GPU needed)
+//   kzg <curve> <n> <hex powers> <hex gamma powers> <hex coeffs> <hex blinding> <hex z> then four (hex xy, infinity) pairs --
+//       commit, hiding commit, open.w, hiding open.w -- and <hex random_v>
 // Byte equality is the bar.  Exit code 0 = all vectors match.
 #include <cstdio>
 #include <fstream>
@@ -68,6 +70,44 @@ static bool run_wmap(int log_n, const std::vector<uint8_t>& a, const std::vector
     std::memcpy(vc.data(), c.data(), n * sizeof(F));
     std::vector<F> h = zkm::witness_map(*dom, va, vb, vc);
     return std::memcmp(h.data(), want.data(), n * sizeof(F)) == 0;
+}
+
+template <class Curve>
+static bool run_kzg(size_t n, const std::vector<uint8_t>& pw, const std::vector<uint8_t>& gpw, const std::vector<uint8_t>& co,
+                    const std::vector<uint8_t>& bl, const std::vector<uint8_t>& z, const std::vector<std::vector<uint8_t>>& want,
+                    const int* want_inf, const std::vector<uint8_t>& want_rv) {
+    typedef zkm::GroupAffine<Curve, 1> A;
+    typedef typename A::Coord Coord;
+    typedef typename Curve::Fr F;
+    auto points = [&](const std::vector<uint8_t>& raw) {
+        std::vector<A> b(n);
+        for (size_t i = 0; i < n; i++) {
+            std::memcpy(&b[i].x, raw.data() + i * 2 * sizeof(Coord), sizeof(Coord));
+            std::memcpy(&b[i].y, raw.data() + i * 2 * sizeof(Coord) + sizeof(Coord), sizeof(Coord));
+            b[i].infinity = false;
+        }
+        return b;
+    };
+    auto elems = [&](const std::vector<uint8_t>& raw) {
+        std::vector<F> v(raw.size() / sizeof(F));
+        std::memcpy(v.data(), raw.data(), raw.size());
+        return v;
+    };
+    auto same = [&](const A& p, int k) {
+        return (int)p.infinity == want_inf[k] && std::memcmp(&p.x, want[k].data(), sizeof(Coord)) == 0 &&
+               std::memcmp(&p.y, want[k].data() + sizeof(Coord), sizeof(Coord)) == 0;
+    };
+    zkm::RegisteredBases<Curve, 1> g(points(pw)), gg(points(gpw), true);
+    std::vector<F> c = elems(co), b = elems(bl);
+    F point = elems(z)[0];
+    bool ok = same(zkm::KZG10::commit<Curve>(g, c), 0) && same(zkm::KZG10::commit<Curve>(g, gg, c, b), 1);
+    auto batch = zkm::KZG10::commit_batch<Curve>(g, {c, b, c});
+    ok = ok && batch.size() == 3 && same(batch[0], 0) && same(batch[2], 0);
+    auto pr = zkm::KZG10::open<Curve>(g, c, point);
+    ok = ok && same(pr.w, 2) && !pr.hiding;
+    auto prh = zkm::KZG10::open<Curve>(g, c, point, &gg, &b);
+    ok = ok && same(prh.w, 3) && prh.hiding && std::memcmp(&prh.random_v, want_rv.data(), sizeof(F)) == 0;
+    return ok;
 }
 
 template <class Curve, int GROUP>
@@ -141,6 +181,16 @@ int main(int argc, char** argv) {
                 ok = curve == "bls12_381" ? run_wmap<zkm::Bls12_381>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh))
                      : curve == "bn254"   ? run_wmap<zkm::Bn254>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh))
                                           : run_wmap<zkm::Bw6_761>(log_n, unhex(ha), unhex(hb), unhex(hc), unhex(hh));
+            } else if (kind == "kzg") {
+                size_t n; std::string hp, hg, hc, hb, hz, hrv;
+                std::vector<std::vector<uint8_t>> want(4);
+                int winf[4];
+                is >> n >> hp >> hg >> hc >> hb >> hz;
+                for (int k = 0; k < 4; k++) { std::string h; is >> h >> winf[k]; want[k] = unhex(h); }
+                is >> hrv;
+                ok = curve == "bls12_381" ? run_kzg<zkm::Bls12_381>(n, unhex(hp), unhex(hg), unhex(hc), unhex(hb), unhex(hz), want, winf, unhex(hrv))
+                     : curve == "bn254"   ? run_kzg<zkm::Bn254>(n, unhex(hp), unhex(hg), unhex(hc), unhex(hb), unhex(hz), want, winf, unhex(hrv))
+                                          : run_kzg<zkm::Bw6_761>(n, unhex(hp), unhex(hg), unhex(hc), unhex(hb), unhex(hz), want, winf, unhex(hrv));
             } else {
                 continue;
             }

@@ -26,7 +26,9 @@ def _build():
 
 
 def _vectors(path):
+    import numpy as np
     from oracle import capi
+    from oracle.py import exact
     lines = []
     for v in json.load(open(os.path.join(HERE, "golden", "ntt_vectors.json")))["vectors"]:
         lines.append("ntt %s %d %d %d %s %s" % (v["curve"], v["log_n"], int(v["inverse"]), int(v["coset"]), v["input"], v["output"]))
@@ -39,8 +41,35 @@ def _vectors(path):
         a, b, c = (capi.random_field_elements(cid, n, seed=s) for s in (21, 22, 23))
         h = capi.witness_map(cid, a, b, c)
         lines.append("wmap %s 9 %s %s %s %s" % (name, a.tobytes().hex(), b.tobytes().hex(), c.tobytes().hex(), h.tobytes().hex()))
+    # KZG10 commit / hiding commit / open / hiding open: expected points from the C++ oracle's MSM over the exact quotient
+    from oracle.py import kzg_exact as kx
+    for cid, name in ((0, "bls12_381"), (1, "bn254"), (2, "bw6_761")):
+        fr = capi.CURVES[cid].fr
+        n = 300
+        pw, gpw = capi.progression(cid, 1, 5, 3, n), capi.progression(cid, 1, 11, 7, n)
+        co, bl = capi.random_field_elements(cid, n, seed=31), capi.random_field_elements(cid, 3, seed=32)
+        zm = capi.random_field_elements(cid, 1, seed=33)
+        ci, bi = ([fr.from_mont(v) for v in capi.limbs_to_ints(a)] for a in (co, bl))
+        zi = fr.from_mont(capi.limbs_to_ints(zm)[0])
+        lim = lambda vals: capi.ints_to_limbs(vals, fr.limbs64)
+        group = exact.Group(capi.CURVES[cid], 1)
+
+        def add(p1, p2):
+            P1 = None if p1[1] else exact.point_from_bytes(capi.CURVES[cid], 1, p1[0].tobytes(), 0)
+            P2 = None if p2[1] else exact.point_from_bytes(capi.CURVES[cid], 1, p2[0].tobytes(), 0)
+            b, f = exact.point_to_bytes(capi.CURVES[cid], 1, group.add(P1, P2))
+            return np.frombuffer(b, dtype=np.uint64), bool(f)
+        c0 = capi.msm(cid, 1, pw, lim(ci))
+        r0 = capi.msm(cid, 1, gpw[:3], lim(bi))
+        w0 = capi.msm(cid, 1, pw[:n - 1], lim(kx.witness_polynomial(fr.modulus, ci, zi)))
+        h0 = capi.msm(cid, 1, gpw[:2], lim(kx.witness_polynomial(fr.modulus, bi, zi)))
+        pts = [c0, add(c0, r0), w0, add(w0, h0)]
+        rv = lim([fr.to_mont(kx.evaluate(fr.modulus, bi, zi))])
+        lines.append("kzg %s %d %s %s %s %s %s %s %s" % (
+            name, n, pw.tobytes().hex(), gpw.tobytes().hex(), co.tobytes().hex(), bl.tobytes().hex(), zm.tobytes().hex(),
+            " ".join("%s %d" % (np.asarray(p[0], dtype=np.uint64).tobytes().hex(), int(p[1])) for p in pts), rv.tobytes().hex()))
     # arkworks compressed serialization (host-only lines, checked before zkm::init)
-    from oracle.py import exact, groth16_exact as gx
+    from oracle.py import groth16_exact as gx
     from oracle.py.params import CURVES
     n_ser = 0
     for name in ("bls12_381", "bn254", "bw6_761"):

@@ -40,6 +40,7 @@ ap.add_argument("--serial", action="store_true", help="run the five MSMs of a pr
 ap.add_argument("--python-threads", action="store_true", help="issue the MSMs from five Python threads instead of one zkm_msm_batch_registered_device call")
 ap.add_argument("--cpu", action="store_true", help="check against / time the CPU restatement of the same work (1 proof)")
 ap.add_argument("--curve", default="bls12_381")
+ap.add_argument("--host-wait", type=int, default=0, help="library option host_wait: 0 auto, 1 spin, 2 block (several replicas per host)")
 ap.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")))
 args = ap.parse_args()
 
@@ -51,6 +52,7 @@ W2 = capi.coord_words(cid, 2)          # ... per G2 coordinate (BW6-761: G2 is o
 SW = capi.fr_words(cid)                # u64 words per Fr element / scalar
 torch.cuda.set_device(args.device)
 zkm.init(args.device)
+zkm.set_option("host_wait", args.host_wait)
 L = _lib.lib()
 dev = torch.device("cuda", args.device)
 rng = np.random.default_rng(7)

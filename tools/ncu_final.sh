@@ -10,6 +10,10 @@ python bench.py --steps 2 --warmup 3 --skip-cpu --skip-proxy --skip-precompute >
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_bench_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --skip-cpu --skip-proxy --skip-precompute > $OUT/ncu_bench_$TAG.log 2>&1
 python tools/profile_target.py 24 > $OUT/pt_plain_$TAG.log 2>&1 || { echo "plain target failed"; exit 1; }
+# DRAM traffic of every launch of the fixed workload -> profiles/roofline_traffic.json (bench.py's `traffic` fields)
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 900 --csv \
+    --log-file $OUT/traffic_$TAG.csv python tools/profile_target.py 24 > $OUT/ncu_traffic_$TAG.log 2>&1
+python tools/ncu_traffic.py $OUT/traffic_$TAG.csv $OUT/roofline_traffic_$TAG.json $TAG > $OUT/ncu_traffic_summary_$TAG.txt 2>&1; tail -5 $OUT/ncu_traffic_summary_$TAG.txt
 cap() { # name regex skip count
   ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o /tmp/prof_$1 -f \
       python tools/profile_target.py 24 > $OUT/ncu_$1_$TAG.log 2>&1

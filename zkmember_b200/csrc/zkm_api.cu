@@ -40,6 +40,7 @@ struct Global {
         std::shared_ptr<BasesReg> reg;
         uint64_t fingerprint;
         uint64_t last_use;
+        uint64_t hits = 0;
     };
     std::mutex cache_mu;
     std::map<CacheKey, CacheEntry> cache;
@@ -483,6 +484,7 @@ static std::shared_ptr<BasesReg> cached_registration(int curve, int group, const
     const size_t rec = 2 * (size_t)coord_words(curve, group) * 8;
     const uint64_t fp = fingerprint(xy, inf, n, rec, opt.msm_cache);
     Global::CacheKey key{curve, group, xy, inf, n};
+    std::shared_ptr<BasesReg> upgrade;       // a small vector that came back: give it window multiples (see below)
     {
         std::lock_guard<std::mutex> lk(g->cache_mu);
         auto it = g->cache.find(key);
@@ -490,12 +492,33 @@ static std::shared_ptr<BasesReg> cached_registration(int curve, int group, const
             if (it->second.fingerprint == fp) {
                 it->second.last_use = ++g->cache_clock;
                 g->cache_hits++;
-                return it->second.reg;
+                it->second.hits++;
+                const BasesReg& r = *it->second.reg;
+                const bool plain = r.parts.size() == 1 && !r.parts[0].d_table;
+                if (!(opt.msm_cache_precompute && plain && it->second.hits == 1 && n <= ((size_t)1 << 18))) return it->second.reg;
+                upgrade = it->second.reg;
+            } else {
+                g->cache_bytes -= it->second.reg->bytes;   // same address, different content: replace
+                g->cache.erase(it);
             }
-            g->cache_bytes -= it->second.reg->bytes;   // same address, different content: replace
-            g->cache.erase(it);
         }
-        g->cache_misses++;
+        if (!upgrade) g->cache_misses++;
+    }
+    if (upgrade) {
+        // Second call with the same bases (a proving key is used for every proof, benches/groth16.rs:107-115): rebuild the
+        // registration from its device copy WITH the window multiples 2^(c w) P_i.  For the small MSMs of zkMember's
+        // circuits (2^15-2^16 points) the Horner chain of c W doublings is half of the time (k_msm_final 1.6 of 3.3 ms at
+        // 2^16); the table removes it.  Not done on the first call: a vector that never comes back would only pay for it.
+        const BasesPart& p0 = upgrade->parts[0];
+        std::shared_ptr<BasesReg> better =
+            build_registration(curve, group, (const uint64_t*)p0.d_xy, p0.d_inf, n, ZKM_REG_PRECOMPUTE);
+        std::lock_guard<std::mutex> lk(g->cache_mu);
+        auto it = g->cache.find(key);
+        if (it != g->cache.end() && it->second.reg == upgrade) {
+            g->cache_bytes += better->bytes - upgrade->bytes;
+            it->second.reg = better;
+        }
+        return better;
     }
     std::shared_ptr<BasesReg> reg = build_registration(curve, group, xy, inf, n, 0);
     std::lock_guard<std::mutex> lk(g->cache_mu);
@@ -1120,9 +1143,14 @@ int32_t zkm_set_option(const char* key, int64_t value) {
         } else if (!strcmp(key, "msm_cache")) {
             if (value < 0 || value > 2) ZKM_FAIL(ZKM_ERR_ARG, "msm_cache must be 0 (off), 1 (sampled fingerprint) or 2 (full fingerprint)");
             o.msm_cache = (int)value;
+        } else if (!strcmp(key, "msm_cache_precompute")) {
+            o.msm_cache_precompute = value ? 1 : 0;
         } else if (!strcmp(key, "msm_cache_max_mb")) {
             if (value < 0) ZKM_FAIL(ZKM_ERR_ARG, "msm_cache_max_mb must be >= 0");
             o.msm_cache_max_mb = value;
+        } else if (!strcmp(key, "host_wait")) {
+            if (value < 0 || value > 2) ZKM_FAIL(ZKM_ERR_ARG, "host_wait must be 0 (auto), 1 (spin) or 2 (block)");
+            o.host_wait = (int)value;
         } else if (!strcmp(key, "spread_host_calls")) {
             o.spread_host_calls = value ? 1 : 0;
         } else {

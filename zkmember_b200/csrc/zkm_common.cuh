@@ -133,7 +133,12 @@ struct Options {
     // records (default: proving keys / SRS are immutable while a prover runs), 2 = fingerprint of every byte.
     int msm_cache = 1;
     int64_t msm_cache_max_mb = 32768;   // cached registrations are evicted least-recently-used above this
+    int msm_cache_precompute = 1;       // cached vectors of <= 2^18 bases get window multiples when they come back
     int spread_host_calls = 0;   // host-pointer NTT / witness-map calls rotate over the initialised devices
+    // how a call waits for its one device read-back (fold depth): 0 = spin while <= 6 lanes of this process are busy, block
+    // otherwise; 1 = always spin; 2 = always block (several prover PROCESSES sharing the host's cores: spinning threads of
+    // one replica starve the launch threads of the others)
+    int host_wait = 0;
 };
 
 // State of one initialised device.

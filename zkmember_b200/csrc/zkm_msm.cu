@@ -468,7 +468,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     // the fastest when few calls are in flight; with many concurrent lanes (batched proofs) the spinning host threads
     // starve each other, so they block on an event instead.
     cudaEvent_t fev;
-    if (busy_lane_count() > 6) {
+    if (c->opt.host_wait == 2 || (c->opt.host_wait == 0 && busy_lane_count() > 6)) {
         if (!c->sync_ev) ZKM_CUDA(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         fev = c->sync_ev;
     } else {

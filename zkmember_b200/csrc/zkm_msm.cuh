@@ -74,8 +74,8 @@ inline uint32_t msm_reduce_group(uint32_t B, uint32_t W) {
 inline size_t msm_contrib_records(int W, uint32_t B) {
     uint32_t per_w = B / msm_reduce_group(B, (uint32_t)W);
     // acc + slice sums (quad path: 256 per slice) + run + the upper levels of the hierarchical reduction (each at most
-    // 1/8 of the level below, acc and run) + 8 per-level window sums
-    return 2 * (size_t)W * per_w + (size_t)W * ((per_w + 255) / 256) + (size_t)W * (per_w / 2 + 64) + 8 * (size_t)W + 16;
+    // 1/4 of the level below, acc and run) + 16 per-level window sums
+    return 2 * (size_t)W * per_w + (size_t)W * ((per_w + 255) / 256) + (size_t)W * (per_w + 64) + 16 * (size_t)W + 16;
 }
 
 const CurveOps* ops_g1_bls();
