@@ -102,6 +102,38 @@ Context* acquire_lane(int dev) {
     }
 }
 
+std::vector<Context*> acquire_lanes(const std::vector<int>& devs) {
+    std::unique_lock<std::mutex> lk(g_lane_mu);
+    if (!g || g->lanes.empty()) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
+    std::vector<int> need(g->lanes.size(), 0);
+    for (int d : devs) {
+        if (d < 0 || d >= (int)g->lanes.size()) ZKM_FAIL(ZKM_ERR_ARG, "device index %d out of range (%zu initialised)", d, g->lanes.size());
+        if (++need[d] > ZKM_NUM_LANES) ZKM_FAIL(ZKM_ERR_ARG, "a single call needs more than %d lanes on device index %d", ZKM_NUM_LANES, d);
+    }
+    for (;;) {
+        if (!g) ZKM_FAIL(ZKM_ERR_NOT_INIT, "library was shut down");
+        bool ok = true;
+        for (size_t d = 0; d < need.size() && ok; d++) {
+            int free_lanes = 0;
+            for (Context* c : g->lanes[d]) free_lanes += c->busy ? 0 : 1;
+            ok = free_lanes >= need[d];
+        }
+        if (ok) {
+            std::vector<Context*> out;
+            for (int d : devs)
+                for (Context* c : g->lanes[d])
+                    if (!c->busy) {
+                        c->busy = true;
+                        c->opt = g->opt;
+                        out.push_back(c);
+                        break;
+                    }
+            return out;
+        }
+        g_lane_cv.wait(lk);
+    }
+}
+
 int busy_lane_count() {
     std::lock_guard<std::mutex> lk(g_lane_mu);
     int n = 0;
@@ -284,23 +316,26 @@ static void msm_reg_host(const std::shared_ptr<BasesReg>& reg, size_t offset, co
         read_back(c, d_out);
         return;
     }
-    LaneGuard home(0);
-    ZKM_CUDA(cudaSetDevice(home.c->device));
-    StreamScope hscope(home.c, home.c->stream);
+    // lane 0: the home lane (gather + final sum on the primary device); lanes 1..: one per shard -- taken together
+    std::vector<int> devs{0};
+    for (const Job& j : jobs) devs.push_back(j.part->dev);
+    MultiLaneGuard lanes(devs);
+    Context* hc = lanes.c[0];
+    ZKM_CUDA(cudaSetDevice(hc->device));
+    StreamScope hscope(hc, hc->stream);
     // k_msm_final / k_points_sum WRITE records with 128-bit stores (16-byte aligned destinations only); records are 8 n + 8
     // bytes long, so only the first slot of a packed array is aligned: the sum goes to offset 0, the gathered records
     // (which are only ever written by copies and read limb by limb) follow from offset `gofs`
     const size_t gofs = (rb + 15) & ~(size_t)15;
-    char* d_gather = (char*)home.c->gather.get(gofs + jobs.size() * rb);
-    const int home_ord = home.c->device;
+    char* d_gather = (char*)hc->gather.get(gofs + jobs.size() * rb);
+    const int home_ord = hc->device;
     std::vector<int32_t> rc(jobs.size(), ZKM_OK);
     std::vector<std::string> msg(jobs.size());
     std::vector<std::thread> th;
     for (size_t i = 0; i < jobs.size(); i++) {
         th.emplace_back([&, i] {
             rc[i] = guarded([&] {
-                LaneGuard lane(jobs[i].part->dev);
-                Context* c = lane.c;
+                Context* c = lanes.c[1 + i];
                 ZKM_CUDA(cudaSetDevice(c->device));
                 StreamScope scope(c, c->stream);
                 uint64_t* d_rec = (uint64_t*)c->io_out.get(rb);
@@ -317,10 +352,10 @@ static void msm_reg_host(const std::shared_ptr<BasesReg>& reg, size_t offset, co
             set_error("shard %zu (device index %d): %s", i, jobs[i].part->dev, msg[i].c_str());
             throw ZkmError{rc[i]};
         }
-    ZKM_CUDA(cudaSetDevice(home.c->device));
+    ZKM_CUDA(cudaSetDevice(hc->device));
     uint64_t* d_sum = (uint64_t*)d_gather;
-    points_sum_run(home.c, r.curve, r.group, (const uint64_t*)(d_gather + gofs), jobs.size(), d_sum, home.c->stream);
-    read_back(home.c, d_sum);
+    points_sum_run(hc, r.curve, r.group, (const uint64_t*)(d_gather + gofs), jobs.size(), d_sum, hc->stream);
+    read_back(hc, d_sum);
 }
 
 // index of the initialised device that owns a device pointer (the caller's "home" device)
@@ -348,11 +383,6 @@ struct DevItem {
     uint64_t* d_out;
 };
 static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t caller_or_null) {
-    LaneGuard hl(home);
-    Context* hc = hl.c;
-    ZKM_CUDA(cudaSetDevice(hc->device));
-    cudaStream_t caller = caller_or_null ? caller_or_null : hc->stream;
-    StreamScope hscope(hc, caller);
     struct Flat { size_t item, k; Job job; };
     std::vector<Flat> flat;
     std::vector<size_t> njobs(items.size()), goff(items.size(), 0);
@@ -366,8 +396,18 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
             gbytes += (jobs.size() * rec_bytes(items[i].reg->curve, items[i].reg->group) + 15) & ~(size_t)15;
         }
     }
+    const bool fast = items.size() == 1 && flat.size() == 1 && flat[0].job.part->dev == home;
+    // lane 0: the home lane; lanes 1..: one per job -- all taken together (no hold-and-wait between concurrent calls)
+    std::vector<int> devs{home};
+    if (!fast)
+        for (const Flat& f : flat) devs.push_back(f.job.part->dev);
+    MultiLaneGuard lanes(devs);
+    Context* hc = lanes.c[0];
+    ZKM_CUDA(cudaSetDevice(hc->device));
+    cudaStream_t caller = caller_or_null ? caller_or_null : hc->stream;
+    StreamScope hscope(hc, caller);
     // fast path: one job on the caller's device -> no threads, no events, the caller's stream itself
-    if (items.size() == 1 && flat.size() == 1 && flat[0].job.part->dev == home) {
+    if (fast) {
         const BasesReg& r = *items[0].reg;
         const size_t sbytes = (size_t)fr_words(r.curve) * 8;
         run_part(hc, r, flat[0].job, (const uint64_t*)((const char*)items[0].d_scalars + flat[0].job.scal_off * sbytes),
@@ -396,8 +436,7 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
                 const DevItem& it = items[fj.item];
                 const BasesReg& r = *it.reg;
                 const size_t sbytes = (size_t)fr_words(r.curve) * 8, rb = rec_bytes(r.curve, r.group);
-                LaneGuard lane(fj.job.part->dev);
-                Context* c = lane.c;
+                Context* c = lanes.c[1 + f];
                 ZKM_CUDA(cudaSetDevice(c->device));
                 cudaStream_t s = c->stream;
                 StreamScope scope(c, s);

@@ -220,6 +220,17 @@ struct LaneGuard {
     LaneGuard& operator=(const LaneGuard&) = delete;
 };
 
+// Several lanes at once, all or nothing: a call that needs a lane per job never holds some while waiting for others,
+// so concurrent multi-lane calls cannot deadlock each other.  devs[i] = device index of lane i.
+std::vector<Context*> acquire_lanes(const std::vector<int>& devs);
+struct MultiLaneGuard {
+    std::vector<Context*> c;
+    explicit MultiLaneGuard(const std::vector<int>& devs) : c(acquire_lanes(devs)) {}
+    ~MultiLaneGuard() { for (Context* x : c) release_lane(x); }
+    MultiLaneGuard(const MultiLaneGuard&) = delete;
+    MultiLaneGuard& operator=(const MultiLaneGuard&) = delete;
+};
+
 Context* ctx();            // lane 0 (non-compute queries); throws ZKM_ERR_NOT_INIT when zkm_init has not succeeded
 inline bool curve_known(int curve) {
     return curve == ZKM_CURVE_BLS12_381 || curve == ZKM_CURVE_BN254 || curve == ZKM_CURVE_BW6_761;

@@ -387,6 +387,42 @@ __global__ void __launch_bounds__(128) k_window_sum_quad(const XYZZ<F>* __restri
     if (threadIdx.x == 0) st_xyzz(out + blockIdx.x, sh[0]);
 }
 
+// Plain sums of the acc arrays of ALL upper levels of the hierarchical reduction in one launch: block (w, level)
+// sums acc_level[w * per .. + per) -> sums[(level + 1) * W + w].  (One k_window_sum_quad launch per level ran them one
+// after another: seven serial ~165 us tree sums at 2^24.)
+struct LevelSums {
+    int n;                 // upper levels
+    uint32_t off[16];      // record offset of the level's acc array inside `upper`
+    uint32_t per[16];      // chunks per window at that level
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_level_sums_quad(const XYZZ<F>* __restrict__ upper, LevelSums ls, uint32_t W,
+                                                         XYZZ<F>* __restrict__ sums) {
+    __shared__ XYZZ<F> sh[32];
+    const uint32_t w = blockIdx.x % W, lvl = blockIdx.x / W;
+    const uint32_t per = ls.per[lvl];
+    const XYZZ<F>* in = upper + ls.off[lvl] + (size_t)w * per;
+    const int q = threadIdx.x & 3;
+    const uint32_t quad = threadIdx.x >> 2;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t t = quad; t < per; t += 32) {
+        XYZZ<F> v = ld_xyzz(in + t);
+        xyzz_add_quad(acc, v, q, mask);
+    }
+    if (q == 0) sh[quad] = acc;
+    __syncthreads();
+    for (uint32_t s = 16; s > 0; s >>= 1) {
+        if (quad < s) {
+            XYZZ<F> a = sh[quad], b = sh[quad + s];
+            xyzz_add_quad(a, b, q, mask);
+            if (q == 0) sh[quad] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(sums + (size_t)(lvl + 1) * W + w, sh[0]);
+}
+
 template <class F>
 __global__ void __launch_bounds__(128)
 k_accum_xyzz_quad(const XYZZ<F>* __restrict__ items, const TaskList tl, XYZZ<F>* __restrict__ out) {
@@ -609,6 +645,8 @@ struct OpsImpl {
             }
             const XYZZ<F>* cur_run = run0;
             uint32_t cur_per = per_w;
+            LevelSums lsum;
+            lsum.n = 0;
             while (cur_per > 1) {
                 const uint32_t Bp = cur_per - 1;                      // chunk t >= 1 has weight t: bucket b = t - 1
                 // upper levels are pure latency (2 gk dependent additions each, little parallel work): short chunks.
@@ -620,12 +658,15 @@ struct OpsImpl {
                 XYZZ<F>* runk = take((size_t)RW * per2);
                 ZKM_LAUNCH(k_reduce_dense_quad<F>, (RW * per2 * 4 + 127) / 128, 128, 0, s, cur_run, cur_per, 1u, Bp, gk, per2, RW,
                            acck, runk);
-                ZKM_LAUNCH(k_window_sum_quad<F>, RW, 128, 0, s, (const XYZZ<F>*)acck, per2, per2, 1u, sums + (size_t)lv.n * RW);
+                lsum.off[lsum.n] = (uint32_t)(acck - upper);
+                lsum.per[lsum.n] = per2;
+                lsum.n++;
                 lv.lg[lv.n] = 31 - __builtin_clz(gk);
                 lv.n++;
                 cur_run = runk;
                 cur_per = per2;
             }
+            if (lsum.n) ZKM_LAUNCH(k_level_sums_quad<F>, RW * lsum.n, 128, 0, s, (const XYZZ<F>*)upper, lsum, RW, sums);
             ZKM_LAUNCH(k_window_combine<F>, (RW * 4 + 127) / 128, 128, 0, s, (const XYZZ<F>*)sums, lv, RW, (XYZZ<F>*)wsum);
         }
         ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.RW, pl.c, d_out);
