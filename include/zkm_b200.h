@@ -28,7 +28,7 @@
  * (ZKM_REG_DEVICE(i), e.g. the G2 query on its own GPU) or sharded over all of them (ZKM_REG_SHARD), and MSMs over
  * such registrations run on every owning GPU at once, partial sums reduced on the caller's device over NVLink P2P.
  * Any host thread may call any entry point concurrently.  Every compute call borrows a LANE of the device it runs on
- * (16 per device: a stream plus grow-only workspaces) for its duration; calls on different lanes overlap on the GPU.
+ * (48 per device: a stream plus grow-only workspaces) for its duration; calls on different lanes overlap on the GPU.
  * A lane keeps its workspaces until zkm_shutdown(): after a 2^24-point MSM that is ~20 GB on that lane, so a few
  * concurrent LARGE MSMs can exhaust HBM (they then fail with ZKM_ERR_OOM, nothing is corrupted).
  * Options (zkm_set_option) are snapshotted when a call starts: changing them never affects a call in flight.
@@ -187,8 +187,11 @@ int32_t zkm_domain_constants(int32_t curve, uint32_t log_n, uint64_t* out5xS64);
  * bench.py times as the kernel-only figure. */
 int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uint32_t log_n,
                        int32_t inverse, int32_t coset, void* stream);
-/* d_out: 2 * W words (affine, Montgomery) followed by one u64 infinity flag (0 | 1).
- * Synchronises once internally (bucket-occupancy read-back that sizes the reduction tree).  If the registration lives
+/* d_out: 2 * W words (affine, Montgomery) followed by one u64 flag word: 0 = finite point, 1 = point at infinity,
+ * 2 = INVALID -- a scalar had bits at or above the modulus width (what the host entry points report as
+ * ZKM_ERR_SCALAR_RANGE; here the check happens on the device and the call has long returned).
+ * Fully asynchronous: a fixed sequence of kernel launches on `stream`, no device read-back, no host wait -- the call
+ * can be captured into a CUDA graph by the caller.  If the registration lives
  * on other devices (ZKM_REG_DEVICE / ZKM_REG_SHARD) the scalar slices and the result records cross NVLink with
  * peer copies and sharded partial sums are added on the caller's device. */
 int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n,
@@ -218,8 +221,7 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
  * "msm_prefetch_fwd" / "msm_prefetch_bwd" (L2 prefetch distance of the level-0 gathers, default 0 = off),
  * "msm_cache" (0 | 1 | 2) and "msm_cache_max_mb" (registration cache of zkm_msm_g1/g2, see there),
  * "spread_host_calls" (0 | 1: host-pointer zkm_ntt / zkm_witness_map calls rotate over the initialised devices),
- * "host_wait" (0 auto | 1 spin | 2 block: how an MSM waits for its one device read-back; 2 when several prover processes
- * share the host's cores).
+ * "host_wait" (accepted and ignored: since round 2 an MSM has no device read-back to wait for).
  * "msm_precompute" is the legacy form of ZKM_REG_PRECOMPUTE (a process-wide switch: prefer the flag).
  * Unknown keys fail with ZKM_ERR_ARG. */
 int32_t zkm_set_option(const char* key, int64_t value);
@@ -230,7 +232,7 @@ int32_t zkm_profile_last_msm(double* ms_out6);
 /* Work counters of the same MSM, read back from the device (exact, not estimated): [0] points, [1] windows, [2] window
  * bits, [3] bucket-list entries (non-zero digits of non-infinity bases), [4..4+L) outputs of each batched-affine level
  * (pairs added at level l = inputs - outputs), [12] L, [13] XYZZ tasks of the accumulation kernel, [14] buckets,
- * [15] fold levels.  bench.py derives the executed field products of the bucket accumulation from these. */
+ * [15] buckets whose partial sums were folded.  bench.py derives the executed field products of the bucket accumulation from these. */
 int32_t zkm_profile_last_msm_counts(uint64_t* out16);
 /* registration cache of zkm_msm_g1/g2: drop every entry / {hits, misses, entries, device bytes} */
 int32_t zkm_msm_cache_clear(void);

@@ -222,6 +222,67 @@ def test_msm_rejects_non_canonical_scalar(zkm):
     with pytest.raises(zkm.ZkmError) as ei:
         zkm.VariableBaseMSM.multi_scalar_mul(bases, scal)
     assert ei.value.code == -5
+    # the next call on the same lanes is unaffected
+    scal[3, 3] = 0
+    want_xy, want_inf = capi.msm(0, 1, bases, scal)
+    _check_point(BLS12_381, 1, zkm.VariableBaseMSM.multi_scalar_mul(bases, scal), want_xy, want_inf)
+
+
+def test_msm_non_canonical_scalar_device_record_and_shards(zkm):
+    """The range check happens on the device (the run never waits for the host): *_device entry points report it as
+    flag word 2 of the result record, host entry points -- also over several parts / the cache -- as ZKM_ERR_SCALAR_RANGE."""
+    import torch
+    n = 3000
+    bases = capi.progression(0, 1, 5, 3, n)
+    scal = capi.random_scalars(0, n, 9)
+    bad = scal.copy()
+    bad[n - 7, 3] = 1 << 63          # bit 255: not below the 255-bit modulus
+    reg = zkm.RegisteredBases("bls12_381", 1, bases)
+    try:
+        d_out = torch.zeros(13, dtype=torch.int64, device="cuda")
+        for s_host, flag in ((bad, 2), (scal, 0)):
+            d_s = torch.from_numpy(s_host.view(np.int64)).cuda()
+            reg.msm_device(d_s.data_ptr(), n, d_out.data_ptr())
+            torch.cuda.synchronize()
+            assert int(d_out.cpu().numpy().view(np.uint64)[-1]) == flag
+        with pytest.raises(zkm.ZkmError) as ei:
+            reg.msm(bad)
+        assert ei.value.code == -5
+        # the literal multi_scalar_mul signature above the cache threshold (n >= 1024)
+        with pytest.raises(zkm.ZkmError) as ei:
+            zkm.VariableBaseMSM.multi_scalar_mul(bases, bad)
+        assert ei.value.code == -5
+        want_xy, want_inf = capi.msm(0, 1, bases, scal)
+        _check_point(BLS12_381, 1, reg.msm(scal), want_xy, want_inf)
+    finally:
+        reg.release()
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+@pytest.mark.parametrize("g", [1, 2])
+@pytest.mark.parametrize("chunk,kind", [(1, "witness"), (2, "uniform"), (3, "witness"), (16, "witness"), (5, "equal")])
+def test_msm_fold_kernels(zkm, curve, g, chunk, kind):
+    """Buckets cut into several tasks: 2..8 partial sums go through k_fold_quad, more through k_fold_cta (one CTA per
+    bucket: strided sums + shared-memory tree).  Tiny task lengths force both paths on every window; `equal` puts every
+    point into one bucket per window (thousands of partial sums in one CTA)."""
+    n = 6000 if g == 1 else 2500
+    bases = capi.progression(curve.curve_id, g, 3, 5, n)
+    if kind == "equal":
+        scal = np.tile(capi.random_scalars(curve.curve_id, 1, seed=chunk), (n, 1))
+    else:
+        scal = capi.random_scalars(curve.curve_id, n, seed=100 + chunk, kind=kind)
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[::97] = 1
+    want_xy, want_inf = capi.msm(curve.curve_id, g, bases, scal, inf)
+    zkm.set_option("msm_chunk", chunk)
+    try:
+        for c_bits in (0, 4, 11):
+            zkm.set_option("msm_window_bits", c_bits)
+            got = zkm.VariableBaseMSM.multi_scalar_mul(bases, scal, curve=curve.name, group=g, infinity=inf)
+            _check_point(curve, g, got, want_xy, want_inf)
+    finally:
+        zkm.set_option("msm_chunk", 0)
+        zkm.set_option("msm_window_bits", 0)
 
 
 @pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)

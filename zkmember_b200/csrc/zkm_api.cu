@@ -85,24 +85,59 @@ int device_count_initialised() {
     return g ? (int)g->devs.size() : 0;
 }
 
-Context* acquire_lane(int dev) {
+// Which free lane of device index `dev` a call gets (g_lane_mu held).  A lane is "free" as soon as the host call that
+// borrowed it has RETURNED -- its GPU work may still be running (MSMs are fully asynchronous), and the next borrower's
+// stream is ordered after it (done_ev: the workspaces are shared).  Always handing out the first free lane would chain
+// independent calls behind one another on the GPU (measured: two proofs in flight no faster than one); rotating over
+// all lanes would allocate workspaces on every one of them (a 2^24-point MSM holds ~20 GB per lane).  So, in order:
+//   1. the lowest lane whose previous work ran on the caller's own stream (stream order already serialises the two
+//      calls: no new dependency, no new memory -- the sequential caller stays on one lane);
+//   2. the lowest lane whose previous work has finished;
+//   3. otherwise the free lanes in turn (the call then waits for that lane's previous work on the GPU).
+static Context* pick_free_lane(int dev, cudaStream_t hint) {
+    static unsigned cursor[64] = {0};
+    auto& v = g->lanes[dev];
+    const size_t L = v.size();
+    if (hint)
+        for (Context* c : v)
+            if (!c->busy && c->last_stream == hint) return c;
+    Context* pick = nullptr;
+    for (Context* c : v) {
+        if (c->busy) continue;
+        if (!c->done_ev || cudaEventQuery(c->done_ev) == cudaSuccess) {
+            pick = c;
+            break;
+        }
+    }
+    cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
+    if (pick) return pick;
+    unsigned& cur = cursor[dev & 63];
+    for (size_t k = 0; k < L; k++) {
+        Context* c = v[(cur + k) % L];
+        if (!c->busy) {
+            cur = (unsigned)((cur + k + 1) % L);
+            return c;
+        }
+    }
+    return nullptr;
+}
+
+Context* acquire_lane(int dev, cudaStream_t hint) {
     std::unique_lock<std::mutex> lk(g_lane_mu);
     if (!g || g->lanes.empty()) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
     if (dev < 0 || dev >= (int)g->lanes.size()) ZKM_FAIL(ZKM_ERR_ARG, "device index %d out of range (%zu initialised)", dev, g->lanes.size());
     for (;;) {
         if (!g) ZKM_FAIL(ZKM_ERR_NOT_INIT, "library was shut down");
-        for (Context* c : g->lanes[dev]) {
-            if (!c->busy) {
-                c->busy = true;
-                c->opt = g->opt;      // snapshot: stable for the whole call whatever zkm_set_option does meanwhile
-                return c;
-            }
+        if (Context* c = pick_free_lane(dev, hint)) {
+            c->busy = true;
+            c->opt = g->opt;      // snapshot: stable for the whole call whatever zkm_set_option does meanwhile
+            return c;
         }
         g_lane_cv.wait(lk);
     }
 }
 
-std::vector<Context*> acquire_lanes(const std::vector<int>& devs) {
+std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t hint0) {
     std::unique_lock<std::mutex> lk(g_lane_mu);
     if (!g || g->lanes.empty()) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
     std::vector<int> need(g->lanes.size(), 0);
@@ -120,14 +155,12 @@ std::vector<Context*> acquire_lanes(const std::vector<int>& devs) {
         }
         if (ok) {
             std::vector<Context*> out;
-            for (int d : devs)
-                for (Context* c : g->lanes[d])
-                    if (!c->busy) {
-                        c->busy = true;
-                        c->opt = g->opt;
-                        out.push_back(c);
-                        break;
-                    }
+            for (size_t i = 0; i < devs.size(); i++) {
+                Context* c = pick_free_lane(devs[i], i == 0 ? hint0 : nullptr);   // cannot fail: the free lanes were counted above
+                c->busy = true;
+                c->opt = g->opt;
+                out.push_back(c);
+            }
             return out;
         }
         g_lane_cv.wait(lk);
@@ -185,6 +218,12 @@ static void h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 }
 
 static size_t rec_bytes(int curve, int group) { return (2 * (size_t)coord_words(curve, group) + 1) * 8; }
+// flag word of a result record read back by a host entry point: 0 finite, 1 infinity, 2 = the MSM saw a scalar with
+// bits at or above the modulus width (detected on the device, reported here: the run itself never waits for the host)
+static uint8_t rec_flag(uint64_t flag) {
+    if (flag == 2) ZKM_FAIL(ZKM_ERR_SCALAR_RANGE, "a scalar has bits at or above the modulus width (not a canonical Fr)");
+    return flag ? 1 : 0;
+}
 
 // ------------------------------------------------------------------------------------------ registrations
 static std::shared_ptr<BasesReg> build_registration(int curve, int group, const uint64_t* xy, const uint8_t* inf, size_t n,
@@ -300,7 +339,7 @@ static void msm_reg_host(const std::shared_ptr<BasesReg>& reg, size_t offset, co
         ZKM_CUDA(cudaMemcpyAsync(h, d_rec, rb, cudaMemcpyDeviceToHost, c->stream));
         ZKM_CUDA(cudaStreamSynchronize(c->stream));
         memcpy(out_xy, h, 2 * (size_t)W * 8);
-        *out_inf = h[2 * W] ? 1 : 0;
+        *out_inf = rec_flag(h[2 * W]);
     };
     if (jobs.size() <= 1) {
         LaneGuard lane(jobs.empty() ? 0 : jobs[0].part->dev);
@@ -401,7 +440,7 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
     std::vector<int> devs{home};
     if (!fast)
         for (const Flat& f : flat) devs.push_back(f.job.part->dev);
-    MultiLaneGuard lanes(devs);
+    MultiLaneGuard lanes(devs, caller_or_null);
     Context* hc = lanes.c[0];
     ZKM_CUDA(cudaSetDevice(hc->device));
     cudaStream_t caller = caller_or_null ? caller_or_null : hc->stream;
@@ -610,7 +649,7 @@ static int32_t msm_direct(int32_t curve, int group, const uint64_t* bases_xy, co
         ZKM_CUDA(cudaMemcpyAsync(h, d_out, (2 * W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
         ZKM_CUDA(cudaStreamSynchronize(c->stream));
         memcpy(out_xy, h, 2 * W * 8);
-        *out_inf = h[2 * W] ? 1 : 0;
+        *out_inf = rec_flag(h[2 * W]);
     });
 }
 
@@ -902,7 +941,7 @@ static void add_two_points(int curve, int group, const uint64_t* a_xy, uint8_t a
     ZKM_CUDA(cudaMemcpyAsync(h + 2 * (W2 + 1), d, rb, cudaMemcpyDeviceToHost, c->stream));
     ZKM_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(out_xy, h + 2 * (W2 + 1), W2 * 8);
-    *out_inf = h[2 * (W2 + 1) + W2] ? 1 : 0;
+    *out_inf = rec_flag(h[2 * (W2 + 1) + W2]);
 }
 
 int32_t zkm_kzg_commit_hiding(uint64_t handle_g, uint64_t handle_gamma_g, const uint64_t* coeffs, size_t n,
@@ -964,7 +1003,7 @@ static void kzg_open_one(const std::shared_ptr<BasesReg>& r, const uint64_t* coe
         ZKM_CUDA(cudaMemcpyAsync(h, d_out, rb, cudaMemcpyDeviceToHost, c->stream));
         ZKM_CUDA(cudaStreamSynchronize(c->stream));
         memcpy(out_xy, h, W2 * 8);
-        *out_inf = h[W2] ? 1 : 0;
+        *out_inf = rec_flag(h[W2]);
     } else {
         // powers sharded over several devices: the quotient (Montgomery) goes back to the host and through the sharded path
         std::vector<uint64_t> q(nq * S);
@@ -1044,7 +1083,7 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
     return guarded([&] {
         check_curve_group(curve, group);
         if (!d_out || (m && !d_points)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(home_device_of(d_out));
+        LaneGuard lane(home_device_of(d_out), (cudaStream_t)stream);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
         points_sum_run(c, curve, group, d_points, m, d_out, stream ? (cudaStream_t)stream : c->stream);
@@ -1076,7 +1115,7 @@ int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uin
                        int32_t coset, void* stream) {
     return guarded([&] {
         if (!d_in || !d_out) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(home_device_of(d_out));
+        LaneGuard lane(home_device_of(d_out), (cudaStream_t)stream);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
         cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
@@ -1088,7 +1127,7 @@ int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uin
 int32_t zkm_fr_into_repr_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream) {
     return guarded([&] {
         if (n && (!d_in || !d_out)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(n ? home_device_of(d_out) : 0);
+        LaneGuard lane(n ? home_device_of(d_out) : 0, (cudaStream_t)stream);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
         fr_into_repr_run(c, curve, d_in, d_out, (uint64_t)n, stream ? (cudaStream_t)stream : c->stream);
@@ -1099,7 +1138,7 @@ int32_t zkm_witness_map_device(int32_t curve, uint64_t* d_a, uint64_t* d_b, uint
                                void* stream) {
     return guarded([&] {
         if (!d_a || !d_b || !d_c || !d_h) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(home_device_of(d_h));
+        LaneGuard lane(home_device_of(d_h), (cudaStream_t)stream);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
         cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;

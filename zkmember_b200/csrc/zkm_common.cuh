@@ -178,10 +178,12 @@ struct Context {
     // The lane's workspaces may still be in use by kernels enqueued on the stream of its previous borrower:
     // every call orders itself after `done_ev` and re-records it when it has enqueued its work.
     cudaEvent_t done_ev = nullptr;
+    cudaStream_t last_stream = nullptr;   // stream of the lane's previous call (lane selection: see pick_free_lane)
     cudaEvent_t sync_ev = nullptr;   // blocking-sync event for host waits while many lanes are busy
     cudaEvent_t spin_ev = nullptr;   // spinning event for the fold-depth read-back
     void begin(cudaStream_t s) {
         if (done_ev) ZKM_CUDA(cudaStreamWaitEvent(s, done_ev, 0));
+        last_stream = s;
     }
     void end(cudaStream_t s) {
         if (!done_ev) ZKM_CUDA(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
@@ -207,14 +209,16 @@ struct StreamScope {
     StreamScope& operator=(const StreamScope&) = delete;
 };
 
-constexpr int ZKM_NUM_LANES = 16;
-Context* acquire_lane(int dev = 0);  // blocks until a lane of device index `dev` is free; throws ZKM_ERR_NOT_INIT before zkm_init
+constexpr int ZKM_NUM_LANES = 48;
+// blocks until a lane of device index `dev` is free; throws ZKM_ERR_NOT_INIT before zkm_init.  `hint`: the stream the
+// call is going to enqueue on, if it is the caller's (a lane last used on that stream is preferred)
+Context* acquire_lane(int dev = 0, cudaStream_t hint = nullptr);
 void release_lane(Context* c);
 int busy_lane_count();
 int device_count_initialised();
 struct LaneGuard {
     Context* c;
-    explicit LaneGuard(int dev = 0) : c(acquire_lane(dev)) {}
+    explicit LaneGuard(int dev = 0, cudaStream_t hint = nullptr) : c(acquire_lane(dev, hint)) {}
     ~LaneGuard() { release_lane(c); }
     LaneGuard(const LaneGuard&) = delete;
     LaneGuard& operator=(const LaneGuard&) = delete;
@@ -222,10 +226,10 @@ struct LaneGuard {
 
 // Several lanes at once, all or nothing: a call that needs a lane per job never holds some while waiting for others,
 // so concurrent multi-lane calls cannot deadlock each other.  devs[i] = device index of lane i.
-std::vector<Context*> acquire_lanes(const std::vector<int>& devs);
+std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t hint0 = nullptr);   // hint0: for devs[0]
 struct MultiLaneGuard {
     std::vector<Context*> c;
-    explicit MultiLaneGuard(const std::vector<int>& devs) : c(acquire_lanes(devs)) {}
+    explicit MultiLaneGuard(const std::vector<int>& devs, cudaStream_t hint0 = nullptr) : c(acquire_lanes(devs, hint0)) {}
     ~MultiLaneGuard() { for (Context* x : c) release_lane(x); }
     MultiLaneGuard(const MultiLaneGuard&) = delete;
     MultiLaneGuard& operator=(const MultiLaneGuard&) = delete;

@@ -13,9 +13,10 @@
 //   K3  k_msm_digits<1>   scatter (point index | sign) into digit-sorted bucket lists
 //       k_tasks_*         cut every bucket list into tasks of <= L entries, order tasks by length
 //   K4  k_accum_affine    one thread per task: XYZZ accumulator += affine base (madd-2008-s), bases
-//                         gathered with 128-bit loads; then k_accum_xyzz levels fold the per-task
-//                         partial sums until every bucket has one sum (keeps skewed inputs -- the
-//                         0/1-heavy Groth16 witness -- balanced without a special case)
+//                         gathered with 128-bit loads; then k_fold_quad / k_fold_cta sum the partial
+//                         sums of every bucket that was cut into several tasks (keeps skewed inputs --
+//                         the 0/1-heavy Groth16 witness -- balanced without a special case and without
+//                         a device read-back)
 //   K5  k_bucket_reduce   running-sum reduction of each window in parallel slices, k_window_sum,
 //       k_msm_final       Horner combine over windows (c doublings each) and normalisation to affine
 // The integer pipe (Montgomery products) bounds K4; everything else is a few percent.  See DESIGN.md.
@@ -38,18 +39,30 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                                                     uint64_t n, MsmPlan pl, int w_only,
                                                     uint32_t* __restrict__ counts_or_cursor,
                                                     uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (inf && inf[i]) continue;
-        const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * SL);
+    // Warp-uniform loop: every lane of a warp walks the digit loop together (lanes without a scalar carry zeros), so
+    // that the lanes hitting the SAME bucket can share one atomic (__match_any_sync).  A Groth16 witness is ~45 % ones:
+    // without the aggregation tens of thousands of atomics serialise on one counter (ncu r2g: 110 us per pass over
+    // 2^16 scalars, 1.1 of the 8.6 ms of kernel time of a proof); the top window of any MSM is skewed the same way.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
+        bool live = i < n && !(inf && inf[i]);
         uint32_t s[SL];
         uint32_t any = 0;
 #pragma unroll
-        for (int v = 0; v < SL / 4; v++) {
-            uint4 a = __ldg(sp + v);
-            s[4 * v] = a.x; s[4 * v + 1] = a.y; s[4 * v + 2] = a.z; s[4 * v + 3] = a.w;
-            any |= a.x | a.y | a.z | a.w;
+        for (int v = 0; v < SL; v++) s[v] = 0;
+        if (live) {
+            const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * SL);
+#pragma unroll
+            for (int v = 0; v < SL / 4; v++) {
+                uint4 a = __ldg(sp + v);
+                s[4 * v] = a.x; s[4 * v + 1] = a.y; s[4 * v + 2] = a.z; s[4 * v + 3] = a.w;
+                any |= a.x | a.y | a.z | a.w;
+            }
         }
-        if (any == 0) continue;
+        live = live && any != 0;
+        if (__ballot_sync(0xffffffffu, live) == 0) continue;
         const uint32_t mask = (1u << pl.c) - 1u;
         uint64_t buf = 0;
         int nb = 0, w = 0;
@@ -73,19 +86,37 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                     sign = 1;
                     carry = 1;
                 }
-                if (d != 0 && (MODE == 0 || w_only < 0 || w == w_only)) {
-                    uint32_t key = (uint32_t)w * pl.key_stride + (d - 1);
-                    if (MODE == 0) {
-                        atomicAdd(&counts_or_cursor[key], 1u);
-                    } else {
-                        uint32_t pos = atomicAdd(&counts_or_cursor[key], 1u);
-                        idx_out[pos] = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (sign << 31);
+                if (MODE == 0 || w_only < 0 || w == w_only) {      // uniform over the warp
+                    const bool hit = live && d != 0;
+                    const uint32_t key = hit ? (uint32_t)w * pl.key_stride + (d - 1) : 0xffffffffu;
+                    const uint32_t entry = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (sign << 31);
+                    if (pl.agg_all || w == 0 || w == pl.W - 1) {
+                        // skew-prone windows (the lowest: scalars 0 / 1 / small; the top: few real bits; every window
+                        // of a small bucket set): lanes with the same bucket share one atomic
+                        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+                        uint32_t pos = 0;
+                        if (hit && lane == leader) pos = atomicAdd(&counts_or_cursor[key], (uint32_t)__popc(peers));
+                        if (MODE == 1) {
+                            pos = __shfl_sync(0xffffffffu, pos, leader);
+                            if (hit) idx_out[pos + (uint32_t)__popc(peers & lt_mask)] = entry;
+                        }
+                    } else if (hit) {
+                        // 2^(c-1) buckets and uniform digits: collisions inside a warp are rare, the match would only
+                        // cost (measured at 2^24, c = 20: sort 5.3 -> 7.0 ms with every window aggregated)
+                        if (MODE == 0) {
+                            atomicAdd(&counts_or_cursor[key], 1u);
+                        } else {
+                            idx_out[atomicAdd(&counts_or_cursor[key], 1u)] = entry;
+                        }
                     }
                 }
                 w++;
             }
         }
-        if (MODE == 0 && (buf != 0 || carry != 0)) atomicOr(&flags[1], 1u);  // scalar wider than the modulus
+        // a canonical scalar is < r < 2^scalar_bits: any bit at or above that position (or a digit carry out of the
+        // top window) marks the input as non-canonical -> flag word 2 of the result record / ZKM_ERR_SCALAR_RANGE
+        if (MODE == 0 && live && (buf != 0 || carry != 0 || (s[SL - 1] >> (pl.scalar_bits & 31)) != 0)) atomicOr(&flags[1], 1u);
     }
 }
 
@@ -97,14 +128,35 @@ __global__ void k_pair_lens(const uint32_t* __restrict__ off_in, uint32_t K, uin
 }
 
 // ---------------------------------------------------------------------------------- task building
-// tpb[k] = ceil(cnt[k] / L); flags[0] = max cnt
+// tpb[k] = ceil(cnt[k] / L); flags[0] = max cnt.  Buckets cut into several tasks are listed for the fold kernels
+// (zkm_msm_curve.cuh): up to ZKM_FOLD_SEG partial sums -> front of fold_list (count in flags[4], k_fold_quad); longer
+// ones -> from the back (fold_list[K - 1 - pos], count in flags[5]) with their partial sums cut into segments of
+// ZKM_FOLD_SEG: seg_first[pos] = first segment, segtab[2 s] = pos, segtab[2 s + 1] = segment number inside the bucket
+// (segment count in flags[6]; k_fold_seg sums every segment, k_fold_cta the segment sums of each bucket).
 __global__ void k_tasks_count(const uint32_t* __restrict__ cnt, uint32_t K, uint32_t L, uint32_t* __restrict__ tpb,
-                              uint32_t* __restrict__ flags) {
+                              uint32_t* __restrict__ flags, uint32_t* __restrict__ fold_list, uint32_t* __restrict__ seg_first,
+                              uint32_t* __restrict__ segtab) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t v = 0;
     if (k < K) {
         v = cnt[k];
-        tpb[k] = (v + L - 1) / L;
+        const uint32_t t = (v + L - 1) / L;
+        tpb[k] = t;
+        if (t > 1) {
+            if (t <= ZKM_FOLD_SEG) {
+                fold_list[atomicAdd(&flags[4], 1u)] = k;
+            } else {
+                const uint32_t nseg = (t + ZKM_FOLD_SEG - 1) / ZKM_FOLD_SEG;
+                const uint32_t pos = atomicAdd(&flags[5], 1u);
+                const uint32_t first = atomicAdd(&flags[6], nseg);
+                fold_list[K - 1 - pos] = k;
+                seg_first[pos] = first;
+                for (uint32_t j = 0; j < nseg; j++) {
+                    segtab[2 * (first + j)] = pos;
+                    segtab[2 * (first + j) + 1] = j;
+                }
+            }
+        }
     } else if (k == K) {
         tpb[k] = 0;
     }
@@ -115,7 +167,7 @@ __global__ void k_tasks_count(const uint32_t* __restrict__ cnt, uint32_t K, uint
     uint32_t wmax = __reduce_max_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0 && wmax) atomicMax(&smax, wmax);
     __syncthreads();
-    if (threadIdx.x == 0 && smax && flags) atomicMax(&flags[0], smax);
+    if (threadIdx.x == 0 && smax) atomicMax(&flags[0], smax);
 }
 
 // per task: owner bucket by binary search in tbase, (start, len), histogram of lengths
@@ -253,8 +305,8 @@ static const CurveOps* curve_ops(int curve, int group) {
 }
 
 enum WsSlot {
-    WS_COUNTS = 0, WS_OFF, WS_CURSOR, WS_IDX, WS_TPB_A, WS_TBASE_A, WS_TPB_B, WS_TBASE_B, WS_TSTART, WS_TLEN,
-    WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_PART_B, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP,
+    WS_COUNTS = 0, WS_OFF, WS_CURSOR, WS_IDX, WS_TPB_A, WS_TBASE_A, WS_FOLDLIST, WS_FOLDSEG, WS_TSTART, WS_TLEN,
+    WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_FOLDSTAGE, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP,
     WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2, WS_XARR
 };
 
@@ -312,6 +364,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         pl.idx_base = 0;
         pl.RW = pl.W;
     }
+    pl.agg_all = pl.K <= 4096 ? 1 : 0;
     if ((double)n * pl.W >= 4.0e9)
         ZKM_FAIL(ZKM_ERR_ARG, "MSM of %zu points x %d windows exceeds 2^32 bucket entries", n, pl.W);
     const uint32_t K = pl.K;
@@ -326,9 +379,6 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         L1 = per_thread < 16 ? 16u : (per_thread > 256 ? 256u : (uint32_t)per_thread);
     }
     if (L1 > 1024) L1 = 1024;
-    // fold fan-in: a chain of f additions per level and log_f levels -- small f minimises the latency of a
-    // small MSM (measured: 2^16 b_g2 8.6 -> 7.5 ms), large f the number of passes over the bucket tables
-    const uint32_t L2 = c->opt.msm_fold > 0 ? (uint32_t)c->opt.msm_fold : (entries < ((size_t)16 << 20) ? 4u : 16u);
     const size_t T1max = entries / L1 + K + 1;
     const size_t XB = ops->xyzz_bytes;
 
@@ -336,16 +386,23 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     uint32_t* off = c->ws[WS_OFF].as<uint32_t>(K + 1);
     uint32_t* cursor = c->ws[WS_CURSOR].as<uint32_t>(K + 1);
     uint32_t* idx = c->ws[WS_IDX].as<uint32_t>(entries);
-    uint32_t* tpb[2] = {c->ws[WS_TPB_A].as<uint32_t>(K + 1), c->ws[WS_TPB_B].as<uint32_t>(K + 1)};
-    uint32_t* tbase[2] = {c->ws[WS_TBASE_A].as<uint32_t>(K + 1), c->ws[WS_TBASE_B].as<uint32_t>(K + 1)};
+    uint32_t* tpb = c->ws[WS_TPB_A].as<uint32_t>(K + 1);
+    uint32_t* tbase = c->ws[WS_TBASE_A].as<uint32_t>(K + 1);
+    uint32_t* fold_list = c->ws[WS_FOLDLIST].as<uint32_t>(K + 1);
+    // segments of the long buckets: a bucket is long with > ZKM_FOLD_SEG tasks and its last segment may be short
+    const size_t max_segs = T1max / ZKM_FOLD_SEG + T1max / (ZKM_FOLD_SEG + 1) + 2;
+    uint32_t* seg_first = c->ws[WS_FOLDSEG].as<uint32_t>(K + 1 + 2 * max_segs);
+    uint32_t* segtab = seg_first + K + 1;
     uint32_t* tstart = c->ws[WS_TSTART].as<uint32_t>(T1max);
     uint32_t* tlen = c->ws[WS_TLEN].as<uint32_t>(T1max);
     uint32_t* order = c->ws[WS_ORDER].as<uint32_t>(T1max);
     uint32_t* lenhist = c->ws[WS_LENHIST].as<uint32_t>(1024 + 2);
     uint32_t* lencur = c->ws[WS_LENCUR].as<uint32_t>(1024 + 2);
-    char* part[2] = {(char*)c->ws[WS_PART_A].get(T1max * XB), (char*)c->ws[WS_PART_B].get((T1max / L2 + K + 1) * XB)};
-    uint32_t* flags = c->ws[WS_FLAGS].as<uint32_t>(4);
-    uint32_t* h_flags = (uint32_t*)c->pin_out.get(64);
+    char* part = (char*)c->ws[WS_PART_A].get(T1max * XB);
+    char* fold_stage = (char*)c->ws[WS_FOLDSTAGE].get(max_segs * XB);
+    // device words: [0] largest list, [1] a scalar has bits above the modulus width, [2] XYZZ tasks (profile),
+    // [4] / [5] buckets for the quad / CTA fold kernel, [6] segments.  Nothing here is read by the host during the run.
+    uint32_t* flags = c->ws[WS_FLAGS].as<uint32_t>(8);
 
     const bool prof = c->opt.profile != 0;
     // work counters of a profiled run (zkm_profile_last_msm_counts): device words read back after the run
@@ -360,7 +417,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     mark(0);
     const unsigned grid_stream = (unsigned)c->sm_count * 8;
     ZKM_CUDA(cudaMemsetAsync(counts, 0, (K + 1) * sizeof(uint32_t), s));
-    ZKM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), s));
+    ZKM_CUDA(cudaMemsetAsync(flags, 0, 8 * sizeof(uint32_t), s));
     const bool wide = fr_words(curve) == 6;   // 377-bit scalars (BW6-761)
     if (wide)
         ZKM_LAUNCH((k_msm_digits<0, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
@@ -457,68 +514,39 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         }
     }
     mark(2);
-    // level-1 task list
-    ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, cur_cnt, K, L1, tpb[0], flags);
-    exclusive_scan(c, tpb[0], tbase[0], K + 1, s);
-    if (prof) ZKM_CUDA(cudaMemcpyAsync(flags + 2, tbase[0] + K, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));  // level-1 task count
-    ZKM_CUDA(cudaMemcpyAsync(h_flags, flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    // The one host read-back: largest bucket -> depth of the fold tree.  Only the fold loop needs it, so the event is
-    // recorded right after the copy and waited for AFTER the level-1 task list and the bucket accumulation have been
-    // enqueued: the GPU keeps working through the host round trip instead of idling behind it.  A spinning wait is
-    // the fastest when few calls are in flight; with many concurrent lanes (batched proofs) the spinning host threads
-    // starve each other, so they block on an event instead.
-    cudaEvent_t fev;
-    if (c->opt.host_wait == 2 || (c->opt.host_wait == 0 && busy_lane_count() > 6)) {
-        if (!c->sync_ev) ZKM_CUDA(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
-        fev = c->sync_ev;
-    } else {
-        if (!c->spin_ev) ZKM_CUDA(cudaEventCreateWithFlags(&c->spin_ev, cudaEventDisableTiming));
-        fev = c->spin_ev;
-    }
-    ZKM_CUDA(cudaEventRecord(fev, s));
-
-    auto build_tasks = [&](const uint32_t* tb, const uint32_t* offs, const uint32_t* cnts, uint32_t L) {
-        ZKM_CUDA(cudaMemsetAsync(lenhist, 0, (L + 1) * sizeof(uint32_t), s));
-        ZKM_LAUNCH(k_tasks_emit, grid_stream, 256, (L + 1) * sizeof(uint32_t), s, tb, K, offs, cnts, L, tstart, tlen,
-                   lenhist);
-        ZKM_LAUNCH(k_len_offsets, 1, 32, 0, s, lenhist, L, lencur);
-        ZKM_LAUNCH(k_tasks_order, grid_stream, 256, 0, s, tlen, tb, K, lencur, order);
-    };
-    // 256 threads, one CTA per SM (the accumulators are register-bound), persistent over the task list
-    const unsigned grid_acc = (unsigned)c->sm_count;
-    build_tasks(tbase[0], cur_off, cur_cnt, L1);
+    // Task list: every bucket list is cut into tasks of <= L1 entries, tasks sorted by length.  Buckets that were cut
+    // (a long list: the skewed top window, the "ones" bucket of a Groth16 witness) get their partial sums folded by the
+    // two fold kernels below -- a fixed launch sequence: the run needs NO device read-back, the host thread never waits
+    // (round 1/2a: log_f levels of {count, scan, emit, order, accumulate} sized from a read-back of the largest list;
+    // 6 levels = 48 launches and ~0.5 of the 3.4 ms of a 2^16-point MSM).
+    ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, cur_cnt, K, L1, tpb, flags, fold_list, seg_first, segtab);
+    exclusive_scan(c, tpb, tbase, K + 1, s);
+    if (prof) ZKM_CUDA(cudaMemcpyAsync(flags + 2, tbase + K, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));  // task count
+    ZKM_CUDA(cudaMemsetAsync(lenhist, 0, (L1 + 1) * sizeof(uint32_t), s));
+    ZKM_LAUNCH(k_tasks_emit, grid_stream, 256, (L1 + 1) * sizeof(uint32_t), s, tbase, K, cur_off, cur_cnt, L1, tstart, tlen,
+               lenhist);
+    ZKM_LAUNCH(k_len_offsets, 1, 32, 0, s, lenhist, L1, lencur);
+    ZKM_LAUNCH(k_tasks_order, grid_stream, 256, 0, s, tlen, tbase, K, lencur, order);
     mark(3);
-    ops->accum_affine(grid_acc, s, cur_src, cur_idx, TaskList{tstart, tlen, order, tbase[0], K}, part[0]);
-
-    mark(4);
-    ZKM_CUDA(cudaEventSynchronize(fev));
-    if (h_flags[1])
-        ZKM_FAIL(ZKM_ERR_SCALAR_RANGE, "a scalar has bits at or above bit %d (not a canonical Fr)", pl.scalar_bits + 1);
-    const uint32_t maxcnt = h_flags[0];
-    int n_folds = 0;
-    int cur = 0;  // tpb[cur] / tbase[cur] / part[cur] describe the current partial sums
-    uint32_t maxseg = (maxcnt + L1 - 1) / L1;
-    while (maxseg > 1) {
-        const int nxt = cur ^ 1;
-        ZKM_LAUNCH(k_tasks_count, kblocks, 256, 0, s, tpb[cur], K, L2, tpb[nxt], (uint32_t*)nullptr);
-        exclusive_scan(c, tpb[nxt], tbase[nxt], K + 1, s);
-        build_tasks(tbase[nxt], tbase[cur], tpb[cur], L2);
-        ops->accum_xyzz(grid_acc, s, part[cur], TaskList{tstart, tlen, order, tbase[nxt], K}, part[nxt],
-                        entries < ((size_t)4 << 20) ? 1 : 0);   // small MSM: latency-bound folds, four lanes per chain
-        cur = nxt;
-        n_folds++;
-        maxseg = (maxseg + L2 - 1) / L2;
+    // One task per thread, persistent over the task list; the accumulators are register-bound (two 128-thread CTAs per
+    // SM).  A small MSM gets only the CTAs its task bound needs: one warp per scheduler (a dependent product is 1.85 k
+    // cycles alone, 2.65 k with two warps per scheduler: tools/microbench/tail_latency.cu) and room on the SMs for the
+    // kernels of concurrent MSMs (CTAs beyond the device-side task count exit at once).
+    {
+        const size_t need = (T1max + 127) / 128, cap = (size_t)c->sm_count * 2;
+        ops->accum_affine((unsigned)(need < cap ? need : cap), s, cur_src, cur_idx, TaskList{tstart, tlen, order, tbase, K}, part);
     }
-
+    mark(4);
+    ops->fold((unsigned)c->sm_count, s, part, tbase, tpb, fold_list, seg_first, segtab, fold_stage, K, (uint32_t)max_segs, flags + 4);
     mark(5);
     void* contrib = c->ws[WS_CONTRIB].get(msm_contrib_records(pl.RW, pl.B) * XB);
     void* wsum = c->ws[WS_WSUM].get((size_t)pl.RW * XB);
-    ops->reduce(s, part[cur], tbase[cur], tpb[cur], pl, contrib, wsum, d_out);
+    ops->reduce(s, part, tbase, tpb, pl, contrib, wsum, flags, d_out);
     mark(6);
     c->pev_valid = prof;
     if (prof) {
         // [0] points, [1] windows, [2] window bits, [3] list entries (non-zero digits), [4..4+L) outputs of each
-        // batched-affine level, [12] affine levels L, [13] level-1 XYZZ tasks, [14] buckets K, [15] fold levels
+        // batched-affine level, [12] affine levels L, [13] XYZZ tasks, [14] buckets K, [15] buckets folded
         for (auto& v : c->pcount) v = 0;
         cnt_words[3] = off + K;
         cnt_words[13] = flags + 2;
@@ -534,7 +562,11 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         c->pcount[2] = (uint64_t)pl.c;
         c->pcount[12] = (uint64_t)n_cnt_levels;
         c->pcount[14] = K;
-        c->pcount[15] = (uint64_t)n_folds;
+        {   // buckets whose partial sums were folded (quad kernel + CTA kernel)
+            uint32_t nf[2] = {0, 0};
+            ZKM_CUDA(cudaMemcpy(nf, flags + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            c->pcount[15] = (uint64_t)nf[0] + nf[1];
+        }
         note_profiled_lane(c);
     }
 }

@@ -20,6 +20,7 @@ struct MsmPlan {
     uint32_t idx_stride;
     uint32_t idx_base;
     int RW;        // windows seen by the reduction: W, or 1 with precomputed multiples (no Horner doublings)
+    int agg_all;   // digit kernels: warp-aggregate the bucket atomics of EVERY window (small bucket sets), not only w = 0 / W - 1
 };
 
 // Task list of one fold level: task t sums entries [tstart[t], tstart[t] + tlen[t]); threads walk
@@ -32,16 +33,23 @@ struct TaskList {
     uint32_t K;
 };
 
+// partial sums per fold segment: a bucket with up to this many is summed by one quad, longer ones segment by segment
+constexpr uint32_t ZKM_FOLD_SEG = 8;
+
 struct CurveOps {
     int curve, group, scalar_bits;
     size_t xyzz_bytes;
     // K4: out[task] = sum of the (sign-adjusted) affine bases named by idx[...]
     void (*accum_affine)(unsigned grid, cudaStream_t s, const void* bases, const uint32_t* idx, TaskList tl, void* out);
-    // fold level: out[task] = sum of XYZZ items
-    void (*accum_xyzz)(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out, int quad);
-    // K5: bucket sums (cnt[k] in {0,1}, item at off[k]) -> affine result record at d_out
+    // fold: bucket k holds tpb[k] partial sums items[tbase[k] ..); afterwards its sum is items[tbase[k]].  fold_list,
+    // seg_first, segtab, n_lists as written by k_tasks_count; `stage` holds one record per segment.
+    void (*fold)(unsigned sm_count, cudaStream_t s, void* items, const uint32_t* tbase, const uint32_t* tpb,
+                 const uint32_t* fold_list, const uint32_t* seg_first, const uint32_t* segtab, void* stage, uint32_t K,
+                 uint32_t max_segs, const uint32_t* n_lists);
+    // K5: bucket sums (cnt[k] != 0: item at off[k]) -> affine result record at d_out; flags[1] != 0 (a scalar was not
+    // canonical) turns the record's flag word into 2
     void (*reduce)(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl, void* contrib,
-                   void* wsum, uint64_t* d_out);
+                   void* wsum, const uint32_t* flags, uint64_t* d_out);
     void (*write_identity)(cudaStream_t s, uint64_t* d_out);
     void (*points_sum)(cudaStream_t s, const uint64_t* d_points, uint64_t m, uint64_t* d_out);
     void (*gen_progression)(cudaStream_t s, uint64_t a0, uint64_t d, uint64_t n, void* d_out);

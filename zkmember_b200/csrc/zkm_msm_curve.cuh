@@ -87,7 +87,7 @@ __device__ __noinline__ bool xyzz_to_affine_ni(const XYZZ<F>& p, F& x, F& y) { r
 
 // ---------------------------------------------------------------------------------- K4 accumulation
 template <class F>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(128, 2)
 k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx, const TaskList tl, XYZZ<F>* __restrict__ out) {
     constexpr int CB = CoordIO<F>::BYTES;
     const uint32_t* __restrict__ tstart = tl.tstart;
@@ -117,25 +117,6 @@ k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx,
             F my = neg(cy);
             if (csign) cy = my;
             if (idx || !aff_is_identity(cx)) xyzz_madd(acc, cx, cy);
-        }
-        st_xyzz(out + task, acc);
-    }
-}
-
-template <class F>
-__global__ void __launch_bounds__(256, 1)
-k_accum_xyzz(const XYZZ<F>* __restrict__ items, const TaskList tl, XYZZ<F>* __restrict__ out) {
-    const uint32_t* __restrict__ tstart = tl.tstart;
-    const uint32_t* __restrict__ tlen = tl.tlen;
-    const uint32_t* __restrict__ order = tl.order;
-    const uint32_t T = tl.tbase[tl.K];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
-        const uint32_t task = order[t];
-        const uint32_t s = tstart[task], len = tlen[task];
-        XYZZ<F> acc = ld_xyzz(items + s);
-        for (uint32_t j = 1; j < len; j++) {
-            XYZZ<F> q = ld_xyzz(items + s + j);
-            xyzz_add(acc, q);
         }
         st_xyzz(out + task, acc);
     }
@@ -293,25 +274,27 @@ __global__ void __launch_bounds__(64) k_window_sum(const XYZZ<F>* __restrict__ i
     if (threadIdx.x == 0) st_xyzz(out + blockIdx.x, sh[0]);
 }
 
-// result record: x, y (Montgomery affine), then one u64 flag (1 = point at infinity; x = 0, y = 1 like
-// ark-ec GroupAffine::zero())
+// result record: x, y (Montgomery affine), then one u64 flag: 0 = finite point, 1 = point at infinity (x = 0, y = 1
+// like ark-ec GroupAffine::zero()), 2 = INVALID: a scalar of the MSM was not canonical (bits at or above the modulus
+// width) -- the host entry points turn it into ZKM_ERR_SCALAR_RANGE, the *_device ones document it (zkm_b200.h)
 template <class F>
-__device__ void write_result(uint64_t* out, const XYZZ<F>& p) {
+__device__ void write_result(uint64_t* out, const XYZZ<F>& p, bool invalid = false) {
     constexpr int CB = CoordIO<F>::BYTES;
     F x, y;
-    bool ok = xyzz_to_affine_ni(p, x, y);
+    bool ok = !invalid && xyzz_to_affine_ni(p, x, y);
     if (!ok) {
         x = F::zero();
         y = F::one();
     }
     CoordIO<F>::st(out, x);
     CoordIO<F>::st(reinterpret_cast<char*>(out) + CB, y);
-    out[2 * CB / 8] = ok ? 0ull : 1ull;
+    out[2 * CB / 8] = invalid ? 2ull : (ok ? 0ull : 1ull);
 }
 
 // ---- lane-cooperative group law for the serial tails (zkm_msm_quad.cuh) and the Horner combine
 template <class F>
-__global__ void k_msm_final(const XYZZ<F>* __restrict__ wsum, int W, int c, uint64_t* __restrict__ out) {
+__global__ void k_msm_final(const XYZZ<F>* __restrict__ wsum, int W, int c, const uint32_t* __restrict__ flags,
+                            uint64_t* __restrict__ out) {
     if (threadIdx.x >= 4 || blockIdx.x != 0) return;
     const int q = threadIdx.x;     // four cooperating lanes, identical state
     const uint32_t mask = 0xfu;
@@ -322,7 +305,7 @@ __global__ void k_msm_final(const XYZZ<F>* __restrict__ wsum, int W, int c, uint
         XYZZ<F> s = ld_xyzz(wsum + w);
         xyzz_add_quad(total, s, q, mask);
     }
-    if (q == 0) write_result<F>(out, total);
+    if (q == 0) write_result<F>(out, total, flags && flags[1] != 0);
 }
 
 // Quad versions of the tail kernels, used when the MSM is small (few thousand chains, all latency): one
@@ -423,24 +406,87 @@ __global__ void __launch_bounds__(128) k_level_sums_quad(const XYZZ<F>* __restri
     if (threadIdx.x == 0) st_xyzz(sums + (size_t)(lvl + 1) * W + w, sh[0]);
 }
 
+// ---- fold: a bucket whose list was cut into several tasks holds several partial sums, consecutive records
+// items[tbase[k] .. tbase[k] + tpb[k]); afterwards the bucket's sum is items[tbase[k]] (in place).  Which buckets:
+// the lists k_tasks_count wrote (zkm_msm.cu) -- the launch sequence is fixed, nothing is read back by the host.
+// Buckets with 2..8 partial sums: one quad each, a chain of <= 7 additions.
 template <class F>
 __global__ void __launch_bounds__(128)
-k_accum_xyzz_quad(const XYZZ<F>* __restrict__ items, const TaskList tl, XYZZ<F>* __restrict__ out) {
-    const uint32_t* __restrict__ tstart = tl.tstart;
-    const uint32_t* __restrict__ tlen = tl.tlen;
-    const uint32_t* __restrict__ order = tl.order;
-    const uint32_t T = tl.tbase[tl.K];
+k_fold_quad(XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ tpb,
+            const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_lists) {
+    const uint32_t nA = n_lists[0];
     const int q = threadIdx.x & 3;
     const uint32_t mask = 0xfu << (threadIdx.x & 28);
-    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; t < T; t += (gridDim.x * blockDim.x) >> 2) {
-        const uint32_t task = order[t];
-        const uint32_t s = tstart[task], len = tlen[task];
-        XYZZ<F> acc = ld_xyzz(items + s);
-        for (uint32_t j = 1; j < len; j++) {
-            XYZZ<F> v = ld_xyzz(items + s + j);
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; i < nA; i += (gridDim.x * blockDim.x) >> 2) {
+        const uint32_t k = list[i];
+        const uint32_t base = tbase[k], cnt = tpb[k];
+        XYZZ<F> acc = ld_xyzz(items + base);
+        for (uint32_t j = 1; j < cnt; j++) {
+            XYZZ<F> v = ld_xyzz(items + base + j);
             xyzz_add_quad(acc, v, q, mask);
         }
-        if (q == 0) st_xyzz(out + task, acc);
+        if (q == 0) st_xyzz(items + base, acc);
+    }
+}
+// Longer buckets (the top window of every MSM, the "ones" bucket of a Groth16 witness: thousands of partial sums):
+// first every segment of ZKM_FOLD_SEG consecutive partial sums by one quad (all segments of all long buckets in
+// parallel over the whole GPU), then one CTA per bucket over its segment sums -- 64 quads take strided subsets, then a
+// tree through shared memory.  1 843 partial sums: 7 + 4 + 6 dependent additions instead of 29 + 6 on one CTA.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fold_seg(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ tpb,
+           const uint32_t* __restrict__ list, const uint32_t* __restrict__ seg_first, const uint32_t* __restrict__ segtab,
+           XYZZ<F>* __restrict__ stage, uint32_t K, const uint32_t* __restrict__ n_lists) {
+    const uint32_t nS = n_lists[2];
+    const int q = threadIdx.x & 3;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    for (uint32_t sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; sgm < nS; sgm += (gridDim.x * blockDim.x) >> 2) {
+        const uint32_t pos = segtab[2 * sgm], j = segtab[2 * sgm + 1];
+        const uint32_t k = list[K - 1 - pos];
+        const uint32_t base = tbase[k] + j * ZKM_FOLD_SEG;
+        uint32_t cnt = tpb[k] - j * ZKM_FOLD_SEG;
+        if (cnt > ZKM_FOLD_SEG) cnt = ZKM_FOLD_SEG;
+        XYZZ<F> acc = ld_xyzz(items + base);
+        for (uint32_t i = 1; i < cnt; i++) {
+            XYZZ<F> v = ld_xyzz(items + base + i);
+            xyzz_add_quad(acc, v, q, mask);
+        }
+        if (q == 0) st_xyzz(stage + seg_first[pos] + j, acc);
+    }
+}
+constexpr int ZKM_FOLD_NT = 256;
+template <class F>
+__global__ void __launch_bounds__(ZKM_FOLD_NT)
+k_fold_cta(XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ tpb,
+           const uint32_t* __restrict__ list, const uint32_t* __restrict__ seg_first, const XYZZ<F>* __restrict__ stage,
+           uint32_t K, const uint32_t* __restrict__ n_lists) {
+    constexpr uint32_t NQ = ZKM_FOLD_NT / 4;
+    __shared__ XYZZ<F> sh[NQ];
+    const uint32_t nB = n_lists[1];
+    const int q = threadIdx.x & 3;
+    const uint32_t quad = threadIdx.x >> 2;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    for (uint32_t b = blockIdx.x; b < nB; b += gridDim.x) {
+        const uint32_t k = list[K - 1 - b];
+        const uint32_t nseg = (tpb[k] + ZKM_FOLD_SEG - 1) / ZKM_FOLD_SEG;
+        const XYZZ<F>* in = stage + seg_first[b];
+        XYZZ<F> acc = XYZZ<F>::identity();
+        for (uint32_t j = quad; j < nseg; j += NQ) {
+            XYZZ<F> v = ld_xyzz(in + j);
+            xyzz_add_quad(acc, v, q, mask);
+        }
+        if (q == 0) sh[quad] = acc;
+        __syncthreads();
+        for (uint32_t st = NQ / 2; st > 0; st >>= 1) {
+            if (quad < st) {
+                XYZZ<F> a = sh[quad], o = sh[quad + st];
+                xyzz_add_quad(a, o, q, mask);
+                if (q == 0) sh[quad] = a;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) st_xyzz(items + tbase[k], sh[0]);
+        __syncthreads();
     }
 }
 
@@ -457,8 +503,10 @@ __global__ void k_points_sum(const uint64_t* __restrict__ pts, uint64_t m, uint6
     constexpr int CB = CoordIO<F>::BYTES;
     constexpr int REC = 2 * CB / 8 + 1;
     XYZZ<F> total = XYZZ<F>::identity();
+    bool invalid = false;
     for (uint64_t i = 0; i < m; i++) {
         const uint64_t* r = pts + i * REC;
+        if (r[REC - 1] == 2) invalid = true;   // a shard saw a non-canonical scalar
         if (r[REC - 1]) continue;
         // records are 8-byte aligned only (odd word count): read limb by limb
         F x, y;
@@ -471,7 +519,7 @@ __global__ void k_points_sum(const uint64_t* __restrict__ pts, uint64_t m, uint6
         }
         xyzz_madd_ni(total, x, y);
     }
-    write_result<F>(out, total);
+    write_result<F>(out, total, invalid);
 }
 
 // synthetic bases with known discrete logs: P_i = (a0 + i d) G, normalised per point
@@ -541,11 +589,22 @@ template <class G>
 struct OpsImpl {
     typedef typename G::F F;
     static void accum_affine(unsigned grid, cudaStream_t s, const void* bases, const uint32_t* idx, TaskList tl, void* out) {
-        ZKM_LAUNCH(k_accum_affine<F>, grid, 256, 0, s, (const char*)bases, idx, tl, (XYZZ<F>*)out);
+        ZKM_LAUNCH(k_accum_affine<F>, grid, 128, 0, s, (const char*)bases, idx, tl, (XYZZ<F>*)out);
     }
-    static void accum_xyzz(unsigned grid, cudaStream_t s, const void* items, TaskList tl, void* out, int quad) {
-        if (quad) ZKM_LAUNCH(k_accum_xyzz_quad<F>, grid * 2, 128, 0, s, (const XYZZ<F>*)items, tl, (XYZZ<F>*)out);
-        else ZKM_LAUNCH(k_accum_xyzz<F>, grid, 256, 0, s, (const XYZZ<F>*)items, tl, (XYZZ<F>*)out);
+    static void fold(unsigned sm_count, cudaStream_t s, void* items, const uint32_t* tbase, const uint32_t* tpb,
+                     const uint32_t* fold_list, const uint32_t* seg_first, const uint32_t* segtab, void* stage, uint32_t K,
+                     uint32_t max_segs, const uint32_t* n_lists) {
+        // persistent grids over device-side counts: CTAs without work exit at once
+        auto quad_grid = [&](uint64_t quads) {
+            const uint64_t need = (quads * 4 + 127) / 128, cap = (uint64_t)sm_count * 4;
+            return (unsigned)(need < cap ? (need ? need : 1) : cap);
+        };
+        ZKM_LAUNCH(k_fold_quad<F>, quad_grid(K), 128, 0, s, (XYZZ<F>*)items, tbase, tpb, fold_list, n_lists);
+        ZKM_LAUNCH(k_fold_seg<F>, quad_grid(max_segs), 128, 0, s, (const XYZZ<F>*)items, tbase, tpb, fold_list, seg_first, segtab,
+                   (XYZZ<F>*)stage, K, n_lists);
+        const unsigned gc = K < sm_count ? K : sm_count;
+        ZKM_LAUNCH(k_fold_cta<F>, gc, ZKM_FOLD_NT, 0, s, (XYZZ<F>*)items, tbase, tpb, fold_list, seg_first, (const XYZZ<F>*)stage, K,
+                   n_lists);
     }
     // persistent grids: exactly the co-resident CTAs (or fewer when the level is small)
     template <class K>
@@ -597,7 +656,7 @@ struct OpsImpl {
         }
     }
     static void reduce(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl,
-                       void* contrib, void* wsum, uint64_t* d_out) {
+                       void* contrib, void* wsum, const uint32_t* flags, uint64_t* d_out) {
         const uint32_t RW = (uint32_t)pl.RW;
         uint32_t g = msm_reduce_group(pl.B, RW);
         uint32_t per_w = pl.B / g;
@@ -669,7 +728,7 @@ struct OpsImpl {
             if (lsum.n) ZKM_LAUNCH(k_level_sums_quad<F>, RW * lsum.n, 128, 0, s, (const XYZZ<F>*)upper, lsum, RW, sums);
             ZKM_LAUNCH(k_window_combine<F>, (RW * 4 + 127) / 128, 128, 0, s, (const XYZZ<F>*)sums, lv, RW, (XYZZ<F>*)wsum);
         }
-        ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.RW, pl.c, d_out);
+        ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.RW, pl.c, flags, d_out);
     }
     static void write_identity(cudaStream_t s, uint64_t* d_out) { ZKM_LAUNCH(k_write_identity<F>, 1, 32, 0, s, d_out); }
     static void points_sum(cudaStream_t s, const uint64_t* pts, uint64_t m, uint64_t* d_out) {
@@ -692,7 +751,7 @@ struct OpsImpl {
         o.scalar_bits = G::SCALAR_BITS;
         o.xyzz_bytes = sizeof(XYZZ<F>);
         o.accum_affine = accum_affine;
-        o.accum_xyzz = accum_xyzz;
+        o.fold = fold;
         o.reduce = reduce;
         o.write_identity = write_identity;
         o.points_sum = points_sum;
