@@ -543,8 +543,8 @@ def main():
     proxy = None
     if not args.skip_proxy:
         torch.cuda.synchronize()
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "90",
-               "--inflight", "3", "--device", str(local_rank)]
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "180",
+               "--inflight", "6", "--device", str(local_rank)]
         if world > 1:
             cmd += ["--host-wait", "2"]      # replicas share the host's cores: block instead of spinning on the read-back
         if rank == 0 and world == 1 and not args.skip_cpu:
@@ -579,8 +579,8 @@ def main():
         torch.cuda.synchronize()
         run_tool("marlin_proxy", ["marlin_proxy.py", "--log-h", "16", "--log-k", "18", "--proofs", "6"]
                  + ([] if args.skip_cpu else ["--cpu"]))
-        run_tool("groth16_proxy_bw6_761", ["groth16_proxy.py", "--curve", "bw6_761", "--log-n", "16", "--proofs", "45",
-                                           "--inflight", "3"])
+        run_tool("groth16_proxy_bw6_761", ["groth16_proxy.py", "--curve", "bw6_761", "--log-n", "16", "--proofs", "48",
+                                           "--inflight", "4"])
 
     # ---- one PROCESS driving all N GPUs through the C ABI (the Rust prover is a single process: zkm_init_mask +
     # ZKM_REG_SHARD; per-device host threads, partial sums gathered over NVLink P2P and added on device 0).  Rank 0 only,

@@ -48,17 +48,24 @@ struct ZkmError {
         ZKM_CUDA(cudaGetLastError());                                        \
     } while (0)
 
-// A growable device buffer (never shrinks; freed at shutdown).
+// A growable device buffer (never shrinks; freed at shutdown).  Growth is STREAM-ORDERED (cudaFreeAsync + cudaMallocAsync
+// on the stream of the call in progress, from the device's default memory pool, whose release threshold zkm_init* raises
+// so that freed blocks stay with the process): no device-wide synchronisation.  The plain cudaFree + cudaMalloc it
+// replaces stalls every stream of the GPU -- with asynchronous MSMs on 48 lanes a lane that met a larger shape for the
+// first time (a G2 MSM on a lane that had only run G1) froze all proofs in flight for milliseconds (measured r2m:
+// 4 proofs in flight 13-20 ms per proof against 3.3 ms with 2).
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    cudaStream_t* cur = nullptr;    // -> Context::cur_stream of the owning lane (nullptr: legacy default stream)
     void* get(size_t bytes) {
         if (bytes > cap) {
-            if (p) ZKM_CUDA(cudaFree(p));
+            cudaStream_t s = cur ? *cur : nullptr;
+            if (p) ZKM_CUDA(cudaFreeAsync(p, s));   // ordered after everything the lane has enqueued so far
             p = nullptr;
             cap = 0;
             size_t want = bytes + (bytes >> 3) + 256;
-            ZKM_CUDA(cudaMalloc(&p, want));
+            ZKM_CUDA(cudaMallocAsync(&p, want, s));
             cap = want;
         }
         return p;
@@ -159,7 +166,14 @@ struct Context {
     int& sm_count;
     Options opt;                           // snapshot taken when the lane was acquired: stable for the whole call
     std::map<uint64_t, void*>& twiddles;
-    explicit Context(Shared* s) : sh(s), device(s->device), sm_count(s->sm_count), twiddles(s->twiddles) {}
+    explicit Context(Shared* s) : sh(s), device(s->device), sm_count(s->sm_count), twiddles(s->twiddles) {
+        DevBuf* all[] = {&ntt_a, &ntt_b, &io_scalars, &io_bases, &io_inf, &io_out, &gather};
+        for (DevBuf* b : all) b->cur = &cur_stream;
+        for (DevBuf& b : ws) b.cur = &cur_stream;
+    }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    cudaStream_t cur_stream = nullptr;     // stream of the call in progress (StreamScope); the lane's own stream otherwise
     int lane_id = 0;
     bool busy = false;
     cudaStream_t stream = nullptr;
@@ -184,6 +198,7 @@ struct Context {
     void begin(cudaStream_t s) {
         if (done_ev) ZKM_CUDA(cudaStreamWaitEvent(s, done_ev, 0));
         last_stream = s;
+        cur_stream = s;
     }
     void end(cudaStream_t s) {
         if (!done_ev) ZKM_CUDA(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));

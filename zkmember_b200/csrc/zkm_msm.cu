@@ -34,35 +34,26 @@ namespace zkm {
 // for window w_only: one launch per window keeps the write set (n x 4 B) inside the 126 MB L2, so the
 // random 4-byte stores merge into full sectors before they reach HBM.
 // SL = 32-bit limbs per scalar: 8 (BigInteger256) or 12 (BigInteger384, BW6-761).
+// (Warp-aggregated atomics -- __match_any_sync on the bucket key -- were measured in round 2 and dropped: same-address
+// atomics are cheap on B200 (a 45 %-ones witness sorts as fast as uniform scalars, profiles/sweep_msm_*_witness_r2l.jsonl),
+// while the match doubled the cost of every window it ran on: sort 5.3 -> 7.0 ms at 2^24 on all windows, 6.1 ms on two.)
 template <int MODE, int SL>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
                                                     uint64_t n, MsmPlan pl, int w_only,
                                                     uint32_t* __restrict__ counts_or_cursor,
                                                     uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags) {
-    // Warp-uniform loop: every lane of a warp walks the digit loop together (lanes without a scalar carry zeros), so
-    // that the lanes hitting the SAME bucket can share one atomic (__match_any_sync).  A Groth16 witness is ~45 % ones:
-    // without the aggregation tens of thousands of atomics serialise on one counter (ncu r2g: 110 us per pass over
-    // 2^16 scalars, 1.1 of the 8.6 ms of kernel time of a proof); the top window of any MSM is skewed the same way.
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = i0 + lane;
-        bool live = i < n && !(inf && inf[i]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (inf && inf[i]) continue;
+        const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * SL);
         uint32_t s[SL];
         uint32_t any = 0;
 #pragma unroll
-        for (int v = 0; v < SL; v++) s[v] = 0;
-        if (live) {
-            const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * SL);
-#pragma unroll
-            for (int v = 0; v < SL / 4; v++) {
-                uint4 a = __ldg(sp + v);
-                s[4 * v] = a.x; s[4 * v + 1] = a.y; s[4 * v + 2] = a.z; s[4 * v + 3] = a.w;
-                any |= a.x | a.y | a.z | a.w;
-            }
+        for (int v = 0; v < SL / 4; v++) {
+            uint4 a = __ldg(sp + v);
+            s[4 * v] = a.x; s[4 * v + 1] = a.y; s[4 * v + 2] = a.z; s[4 * v + 3] = a.w;
+            any |= a.x | a.y | a.z | a.w;
         }
-        live = live && any != 0;
-        if (__ballot_sync(0xffffffffu, live) == 0) continue;
+        if (any == 0) continue;
         const uint32_t mask = (1u << pl.c) - 1u;
         uint64_t buf = 0;
         int nb = 0, w = 0;
@@ -86,29 +77,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                     sign = 1;
                     carry = 1;
                 }
-                if (MODE == 0 || w_only < 0 || w == w_only) {      // uniform over the warp
-                    const bool hit = live && d != 0;
-                    const uint32_t key = hit ? (uint32_t)w * pl.key_stride + (d - 1) : 0xffffffffu;
-                    const uint32_t entry = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (sign << 31);
-                    if (pl.agg_all || w == 0 || w == pl.W - 1) {
-                        // skew-prone windows (the lowest: scalars 0 / 1 / small; the top: few real bits; every window
-                        // of a small bucket set): lanes with the same bucket share one atomic
-                        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-                        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
-                        uint32_t pos = 0;
-                        if (hit && lane == leader) pos = atomicAdd(&counts_or_cursor[key], (uint32_t)__popc(peers));
-                        if (MODE == 1) {
-                            pos = __shfl_sync(0xffffffffu, pos, leader);
-                            if (hit) idx_out[pos + (uint32_t)__popc(peers & lt_mask)] = entry;
-                        }
-                    } else if (hit) {
-                        // 2^(c-1) buckets and uniform digits: collisions inside a warp are rare, the match would only
-                        // cost (measured at 2^24, c = 20: sort 5.3 -> 7.0 ms with every window aggregated)
-                        if (MODE == 0) {
-                            atomicAdd(&counts_or_cursor[key], 1u);
-                        } else {
-                            idx_out[atomicAdd(&counts_or_cursor[key], 1u)] = entry;
-                        }
+                if (d != 0 && (MODE == 0 || w_only < 0 || w == w_only)) {
+                    uint32_t key = (uint32_t)w * pl.key_stride + (d - 1);
+                    if (MODE == 0) {
+                        atomicAdd(&counts_or_cursor[key], 1u);
+                    } else {
+                        uint32_t pos = atomicAdd(&counts_or_cursor[key], 1u);
+                        idx_out[pos] = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (sign << 31);
                     }
                 }
                 w++;
@@ -116,7 +91,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
         }
         // a canonical scalar is < r < 2^scalar_bits: any bit at or above that position (or a digit carry out of the
         // top window) marks the input as non-canonical -> flag word 2 of the result record / ZKM_ERR_SCALAR_RANGE
-        if (MODE == 0 && live && (buf != 0 || carry != 0 || (s[SL - 1] >> (pl.scalar_bits & 31)) != 0)) atomicOr(&flags[1], 1u);
+        if (MODE == 0 && (buf != 0 || carry != 0 || (s[SL - 1] >> (pl.scalar_bits & 31)) != 0)) atomicOr(&flags[1], 1u);
     }
 }
 
@@ -129,10 +104,12 @@ __global__ void k_pair_lens(const uint32_t* __restrict__ off_in, uint32_t K, uin
 
 // ---------------------------------------------------------------------------------- task building
 // tpb[k] = ceil(cnt[k] / L); flags[0] = max cnt.  Buckets cut into several tasks are listed for the fold kernels
-// (zkm_msm_curve.cuh): up to ZKM_FOLD_SEG partial sums -> front of fold_list (count in flags[4], k_fold_quad); longer
-// ones -> from the back (fold_list[K - 1 - pos], count in flags[5]) with their partial sums cut into segments of
-// ZKM_FOLD_SEG: seg_first[pos] = first segment, segtab[2 s] = pos, segtab[2 s + 1] = segment number inside the bucket
-// (segment count in flags[6]; k_fold_seg sums every segment, k_fold_cta the segment sums of each bucket).
+// (zkm_msm_curve.cuh) in three classes by their number t of partial sums, S = ZKM_FOLD_SEG:
+//   A  2 <= t <= S      fold_list[i], i < flags[4]                     one quad sums them in place
+//   M  S < t <= S^2     fold_list[K + 1 + i], i < flags[7]             segment sums, then one quad over the <= S segments
+//   L  t > S^2          fold_list[K - 1 - i], i < flags[5]             segment sums, then one CTA per bucket
+// Segments (S consecutive partial sums) of M and L buckets: seg_first[k] = first segment of bucket k, segtab[2 s] = k,
+// segtab[2 s + 1] = segment number inside the bucket, flags[6] = segments in all.
 __global__ void k_tasks_count(const uint32_t* __restrict__ cnt, uint32_t K, uint32_t L, uint32_t* __restrict__ tpb,
                               uint32_t* __restrict__ flags, uint32_t* __restrict__ fold_list, uint32_t* __restrict__ seg_first,
                               uint32_t* __restrict__ segtab) {
@@ -147,12 +124,12 @@ __global__ void k_tasks_count(const uint32_t* __restrict__ cnt, uint32_t K, uint
                 fold_list[atomicAdd(&flags[4], 1u)] = k;
             } else {
                 const uint32_t nseg = (t + ZKM_FOLD_SEG - 1) / ZKM_FOLD_SEG;
-                const uint32_t pos = atomicAdd(&flags[5], 1u);
                 const uint32_t first = atomicAdd(&flags[6], nseg);
-                fold_list[K - 1 - pos] = k;
-                seg_first[pos] = first;
+                if (nseg <= ZKM_FOLD_SEG) fold_list[K + 1 + atomicAdd(&flags[7], 1u)] = k;
+                else fold_list[K - 1 - atomicAdd(&flags[5], 1u)] = k;
+                seg_first[k] = first;
                 for (uint32_t j = 0; j < nseg; j++) {
-                    segtab[2 * (first + j)] = pos;
+                    segtab[2 * (first + j)] = k;
                     segtab[2 * (first + j) + 1] = j;
                 }
             }
@@ -364,7 +341,6 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         pl.idx_base = 0;
         pl.RW = pl.W;
     }
-    pl.agg_all = pl.K <= 4096 ? 1 : 0;
     if ((double)n * pl.W >= 4.0e9)
         ZKM_FAIL(ZKM_ERR_ARG, "MSM of %zu points x %d windows exceeds 2^32 bucket entries", n, pl.W);
     const uint32_t K = pl.K;
@@ -388,7 +364,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     uint32_t* idx = c->ws[WS_IDX].as<uint32_t>(entries);
     uint32_t* tpb = c->ws[WS_TPB_A].as<uint32_t>(K + 1);
     uint32_t* tbase = c->ws[WS_TBASE_A].as<uint32_t>(K + 1);
-    uint32_t* fold_list = c->ws[WS_FOLDLIST].as<uint32_t>(K + 1);
+    uint32_t* fold_list = c->ws[WS_FOLDLIST].as<uint32_t>(2 * ((size_t)K + 1));
     // segments of the long buckets: a bucket is long with > ZKM_FOLD_SEG tasks and its last segment may be short
     const size_t max_segs = T1max / ZKM_FOLD_SEG + T1max / (ZKM_FOLD_SEG + 1) + 2;
     uint32_t* seg_first = c->ws[WS_FOLDSEG].as<uint32_t>(K + 1 + 2 * max_segs);
@@ -401,7 +377,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     char* part = (char*)c->ws[WS_PART_A].get(T1max * XB);
     char* fold_stage = (char*)c->ws[WS_FOLDSTAGE].get(max_segs * XB);
     // device words: [0] largest list, [1] a scalar has bits above the modulus width, [2] XYZZ tasks (profile),
-    // [4] / [5] buckets for the quad / CTA fold kernel, [6] segments.  Nothing here is read by the host during the run.
+    // [4] / [7] / [5] fold classes A / M / L, [6] segments.  Nothing here is read by the host during the run.
     uint32_t* flags = c->ws[WS_FLAGS].as<uint32_t>(8);
 
     const bool prof = c->opt.profile != 0;
@@ -563,9 +539,9 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         c->pcount[12] = (uint64_t)n_cnt_levels;
         c->pcount[14] = K;
         {   // buckets whose partial sums were folded (quad kernel + CTA kernel)
-            uint32_t nf[2] = {0, 0};
-            ZKM_CUDA(cudaMemcpy(nf, flags + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-            c->pcount[15] = (uint64_t)nf[0] + nf[1];
+            uint32_t nf[4] = {0, 0, 0, 0};
+            ZKM_CUDA(cudaMemcpy(nf, flags + 4, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            c->pcount[15] = (uint64_t)nf[0] + nf[1] + nf[3];
         }
         note_profiled_lane(c);
     }

@@ -20,7 +20,6 @@ struct MsmPlan {
     uint32_t idx_stride;
     uint32_t idx_base;
     int RW;        // windows seen by the reduction: W, or 1 with precomputed multiples (no Horner doublings)
-    int agg_all;   // digit kernels: warp-aggregate the bucket atomics of EVERY window (small bucket sets), not only w = 0 / W - 1
 };
 
 // Task list of one fold level: task t sums entries [tstart[t], tstart[t] + tlen[t]); threads walk

@@ -408,41 +408,24 @@ __global__ void __launch_bounds__(128) k_level_sums_quad(const XYZZ<F>* __restri
 
 // ---- fold: a bucket whose list was cut into several tasks holds several partial sums, consecutive records
 // items[tbase[k] .. tbase[k] + tpb[k]); afterwards the bucket's sum is items[tbase[k]] (in place).  Which buckets:
-// the lists k_tasks_count wrote (zkm_msm.cu) -- the launch sequence is fixed, nothing is read back by the host.
-// Buckets with 2..8 partial sums: one quad each, a chain of <= 7 additions.
-template <class F>
-__global__ void __launch_bounds__(128)
-k_fold_quad(XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ tpb,
-            const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_lists) {
-    const uint32_t nA = n_lists[0];
-    const int q = threadIdx.x & 3;
-    const uint32_t mask = 0xfu << (threadIdx.x & 28);
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; i < nA; i += (gridDim.x * blockDim.x) >> 2) {
-        const uint32_t k = list[i];
-        const uint32_t base = tbase[k], cnt = tpb[k];
-        XYZZ<F> acc = ld_xyzz(items + base);
-        for (uint32_t j = 1; j < cnt; j++) {
-            XYZZ<F> v = ld_xyzz(items + base + j);
-            xyzz_add_quad(acc, v, q, mask);
-        }
-        if (q == 0) st_xyzz(items + base, acc);
-    }
-}
-// Longer buckets (the top window of every MSM, the "ones" bucket of a Groth16 witness: thousands of partial sums):
-// first every segment of ZKM_FOLD_SEG consecutive partial sums by one quad (all segments of all long buckets in
-// parallel over the whole GPU), then one CTA per bucket over its segment sums -- 64 quads take strided subsets, then a
-// tree through shared memory.  1 843 partial sums: 7 + 4 + 6 dependent additions instead of 29 + 6 on one CTA.
+// the class lists k_tasks_count wrote (zkm_msm.cu; S = ZKM_FOLD_SEG) -- the launch sequence is fixed, nothing is read
+// back by the host.  n_lists = flags + 4: [0] |A|, [1] |L|, [2] segments, [3] |M|.
+//   k_fold_seg   every segment of S consecutive partial sums of the M and L buckets -> stage[] (one quad each, all
+//                segments of all buckets in parallel over the whole GPU)
+//   k_fold_quad  class A: one quad sums the <= S partial sums in place; class M: one quad sums the <= S segment sums
+//   k_fold_cta   class L (the top window of an MSM, the "ones" bucket of a Groth16 witness: thousands of partial
+//                sums): one CTA per bucket over its segment sums, 64 quads take strided subsets, then a tree through
+//                shared memory.  1 843 partial sums: 7 + 4 + 6 dependent additions.
 template <class F>
 __global__ void __launch_bounds__(128)
 k_fold_seg(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ tpb,
-           const uint32_t* __restrict__ list, const uint32_t* __restrict__ seg_first, const uint32_t* __restrict__ segtab,
-           XYZZ<F>* __restrict__ stage, uint32_t K, const uint32_t* __restrict__ n_lists) {
+           const uint32_t* __restrict__ seg_first, const uint32_t* __restrict__ segtab, XYZZ<F>* __restrict__ stage,
+           const uint32_t* __restrict__ n_lists) {
     const uint32_t nS = n_lists[2];
     const int q = threadIdx.x & 3;
     const uint32_t mask = 0xfu << (threadIdx.x & 28);
     for (uint32_t sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; sgm < nS; sgm += (gridDim.x * blockDim.x) >> 2) {
-        const uint32_t pos = segtab[2 * sgm], j = segtab[2 * sgm + 1];
-        const uint32_t k = list[K - 1 - pos];
+        const uint32_t k = segtab[2 * sgm], j = segtab[2 * sgm + 1];
         const uint32_t base = tbase[k] + j * ZKM_FOLD_SEG;
         uint32_t cnt = tpb[k] - j * ZKM_FOLD_SEG;
         if (cnt > ZKM_FOLD_SEG) cnt = ZKM_FOLD_SEG;
@@ -451,7 +434,29 @@ k_fold_seg(const XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase
             XYZZ<F> v = ld_xyzz(items + base + i);
             xyzz_add_quad(acc, v, q, mask);
         }
-        if (q == 0) st_xyzz(stage + seg_first[pos] + j, acc);
+        if (q == 0) st_xyzz(stage + seg_first[k] + j, acc);
+    }
+}
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fold_quad(XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ tpb,
+            const uint32_t* __restrict__ list, const uint32_t* __restrict__ seg_first, const XYZZ<F>* __restrict__ stage,
+            uint32_t K, const uint32_t* __restrict__ n_lists) {
+    const uint32_t nA = n_lists[0], nM = n_lists[3];
+    const int q = threadIdx.x & 3;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; i < nA + nM; i += (gridDim.x * blockDim.x) >> 2) {
+        const bool mid = i >= nA;
+        const uint32_t k = mid ? list[K + 1 + (i - nA)] : list[i];
+        const uint32_t dst = tbase[k];
+        const XYZZ<F>* src = mid ? stage + seg_first[k] : items + dst;
+        const uint32_t cnt = mid ? (tpb[k] + ZKM_FOLD_SEG - 1) / ZKM_FOLD_SEG : tpb[k];
+        XYZZ<F> acc = ld_xyzz(src);
+        for (uint32_t j = 1; j < cnt; j++) {
+            XYZZ<F> v = ld_xyzz(src + j);
+            xyzz_add_quad(acc, v, q, mask);
+        }
+        if (q == 0) st_xyzz(items + dst, acc);
     }
 }
 constexpr int ZKM_FOLD_NT = 256;
@@ -462,14 +467,14 @@ k_fold_cta(XYZZ<F>* __restrict__ items, const uint32_t* __restrict__ tbase, cons
            uint32_t K, const uint32_t* __restrict__ n_lists) {
     constexpr uint32_t NQ = ZKM_FOLD_NT / 4;
     __shared__ XYZZ<F> sh[NQ];
-    const uint32_t nB = n_lists[1];
+    const uint32_t nL = n_lists[1];
     const int q = threadIdx.x & 3;
     const uint32_t quad = threadIdx.x >> 2;
     const uint32_t mask = 0xfu << (threadIdx.x & 28);
-    for (uint32_t b = blockIdx.x; b < nB; b += gridDim.x) {
+    for (uint32_t b = blockIdx.x; b < nL; b += gridDim.x) {
         const uint32_t k = list[K - 1 - b];
         const uint32_t nseg = (tpb[k] + ZKM_FOLD_SEG - 1) / ZKM_FOLD_SEG;
-        const XYZZ<F>* in = stage + seg_first[b];
+        const XYZZ<F>* in = stage + seg_first[k];
         XYZZ<F> acc = XYZZ<F>::identity();
         for (uint32_t j = quad; j < nseg; j += NQ) {
             XYZZ<F> v = ld_xyzz(in + j);
@@ -599,9 +604,10 @@ struct OpsImpl {
             const uint64_t need = (quads * 4 + 127) / 128, cap = (uint64_t)sm_count * 4;
             return (unsigned)(need < cap ? (need ? need : 1) : cap);
         };
-        ZKM_LAUNCH(k_fold_quad<F>, quad_grid(K), 128, 0, s, (XYZZ<F>*)items, tbase, tpb, fold_list, n_lists);
-        ZKM_LAUNCH(k_fold_seg<F>, quad_grid(max_segs), 128, 0, s, (const XYZZ<F>*)items, tbase, tpb, fold_list, seg_first, segtab,
-                   (XYZZ<F>*)stage, K, n_lists);
+        ZKM_LAUNCH(k_fold_seg<F>, quad_grid(max_segs), 128, 0, s, (const XYZZ<F>*)items, tbase, tpb, seg_first, segtab,
+                   (XYZZ<F>*)stage, n_lists);
+        ZKM_LAUNCH(k_fold_quad<F>, quad_grid(K), 128, 0, s, (XYZZ<F>*)items, tbase, tpb, fold_list, seg_first,
+                   (const XYZZ<F>*)stage, K, n_lists);
         const unsigned gc = K < sm_count ? K : sm_count;
         ZKM_LAUNCH(k_fold_cta<F>, gc, ZKM_FOLD_NT, 0, s, (XYZZ<F>*)items, tbase, tpb, fold_list, seg_first, (const XYZZ<F>*)stage, K,
                    n_lists);
