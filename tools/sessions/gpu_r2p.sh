@@ -1,0 +1,34 @@
+#!/bin/bash
+# GPU session r2p: r2o again with the coalesced k_pair_map and the two-stage plain sums of the hierarchical reduction.
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "msm" > gpurun_out/pytest_r2p.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/pytest_r2p.log
+sw() { out=$1; shift; timeout 900 python tools/sweep.py "$@" --reps 5 >> gpurun_out/$out 2>> gpurun_out/r2p.err; }
+: > gpurun_out/sweep_msm_bls12_381_g1_r2p.jsonl; : > gpurun_out/sweep_msm_bn254_g1_r2p.jsonl; : > gpurun_out/tune_pair_r2p.jsonl
+sw sweep_msm_bls12_381_g1_r2p.jsonl msm --curve bls12_381 --min 16 --max 24
+sw sweep_msm_bn254_g1_r2p.jsonl msm --curve bn254 --min 22 --max 24
+python - <<'PY'
+import json, glob
+for f in ["sweep_msm_bls12_381_g1_r2p", "sweep_msm_bn254_g1_r2p", "tune_pair_r2p"]:
+    for l in open("gpurun_out/%s.jsonl" % f):
+        r = json.loads(l); print(f, r["log_n"], round(r["ms"], 3), r.get("window_bits"), r.get("opts"), {k: round(v, 2) for k, v in (r.get("stage_ms") or {}).items()}, r.get("check"))
+PY
+python tools/profile_target.py 24 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/traffic_r2p.csv python tools/profile_target.py 24 > gpurun_out/ncu_traffic_r2p.log 2>&1
+python - <<'PY'
+import csv, collections
+rows = [r for r in csv.reader(open("gpurun_out/traffic_r2p.csv")) if len(r) > 10 and r[0].isdigit()]
+byid = collections.OrderedDict()
+for r in rows:
+    d = byid.setdefault(r[0], {"name": r[4]}); d[r[12]] = float(r[14]); d["u_" + r[12]] = r[13]
+ids = list(byid)
+fin = [i for i in ids if "k_msm_final" in byid[i]["name"]]
+lo, hi = ids.index(fin[-2]) + 1, ids.index(fin[-1]) + 1
+agg = collections.OrderedDict()
+for i in ids[lo:hi]:
+    d = byid[i]; k = d["name"].split("(")[0].replace("void ", "").replace("zkm::", "")[:44]
+    a = agg.setdefault(k, [0, 0, 0, 0]); a[0] += d.get("gpu__time_duration.sum", 0); a[1] += d.get("dram__bytes_read.sum", 0); a[2] += d.get("dram__bytes_write.sum", 0); a[3] += 1
+print("units:", {k: v for k, v in byid[ids[lo]].items() if k.startswith("u_")})
+for k, v in agg.items(): print("  %-46s t=%12.1f rd=%14.1f wr=%14.1f x%d" % (k, v[0], v[1], v[2], v[3]))
+PY
+tail -3 gpurun_out/r2p.err

@@ -102,6 +102,51 @@ __global__ void k_pair_lens(const uint32_t* __restrict__ off_in, uint32_t K, uin
     else if (k == K) len_out[k] = 0;
 }
 
+// Where every output of a pairwise level finds its inputs: map[e] = first input position | (two inputs ? 1 << 31 : 0)
+// for output e of bucket k, e in [off_out[k], off_out[k+1]): inputs off_in[k] + 2 (e - off_out[k]) and the next one (the
+// odd element at the end of a list is passed through).  One thread walks ZKM_MAP_M consecutive outputs with a bucket
+// cursor (one binary search per thread); the CTA's 8192 words go through shared memory so that the stores are
+// contiguous (written straight from the threads -- 32 words 128 bytes apart per store -- the four launches of a
+// 2^24-point MSM took 2.0 ms).  The pair kernels (zkm_msm_affine.cuh) then need neither offsets nor a search and can
+// take the outputs in any order.
+constexpr uint32_t ZKM_MAP_M = 32;
+__global__ void __launch_bounds__(256) k_pair_map(const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
+                                                  uint32_t K, uint32_t* __restrict__ map) {
+    __shared__ uint32_t sh[256 * (ZKM_MAP_M + 1)];
+    const uint32_t E = off_out[K];
+    const uint32_t per_cta = 256 * ZKM_MAP_M;
+    for (uint64_t base = (uint64_t)blockIdx.x * per_cta; base < E; base += (uint64_t)gridDim.x * per_cta) {
+        const uint64_t e0_64 = base + (uint64_t)threadIdx.x * ZKM_MAP_M;
+        if (e0_64 < E) {
+            const uint32_t e0 = (uint32_t)e0_64, e1 = (E - e0 > ZKM_MAP_M) ? e0 + ZKM_MAP_M : E;
+            uint32_t a = 0, b = K;  // off_out[a] <= e0 < off_out[b]
+            while (b - a > 1) {
+                const uint32_t mid = (a + b) >> 1;
+                if (off_out[mid] <= e0) a = mid; else b = mid;
+            }
+            uint32_t k = a, lo = off_out[a], hi = off_out[a + 1];
+            uint32_t ib = off_in[k], ie = off_in[k + 1];
+            for (uint32_t e = e0; e < e1; e++) {
+                while (e >= hi) {
+                    k++;
+                    lo = hi;
+                    hi = off_out[k + 1];
+                    ib = ie;
+                    ie = off_in[k + 1];
+                }
+                const uint32_t i0 = ib + 2 * (e - lo);
+                sh[threadIdx.x * (ZKM_MAP_M + 1) + (e - e0)] = i0 | ((i0 + 1 < ie) ? 0x80000000u : 0u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < per_cta; i += 256) {
+            const uint64_t e = base + i;
+            if (e < E) map[e] = sh[(i / ZKM_MAP_M) * (ZKM_MAP_M + 1) + (i % ZKM_MAP_M)];
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------- task building
 // tpb[k] = ceil(cnt[k] / L); flags[0] = max cnt.  Buckets cut into several tasks are listed for the fold kernels
 // (zkm_msm_curve.cuh) in three classes by their number t of partial sums, S = ZKM_FOLD_SEG:
@@ -284,7 +329,7 @@ static const CurveOps* curve_ops(int curve, int group) {
 enum WsSlot {
     WS_COUNTS = 0, WS_OFF, WS_CURSOR, WS_IDX, WS_TPB_A, WS_TBASE_A, WS_FOLDLIST, WS_FOLDSEG, WS_TSTART, WS_TLEN,
     WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_FOLDSTAGE, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP,
-    WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2, WS_XARR
+    WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2, WS_XARR, WS_PAIRMAP
 };
 
 static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t count, cudaStream_t s) {
@@ -443,7 +488,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
             const double mads = (2.0 * limbs * limbs + limbs) * (group == 2 && curve != ZKM_CURVE_BW6_761 ? 3.0 : 1.0);
             const double scale = mads < 300.0 ? 300.0 / mads : 1.0;   // 1 for BLS12-381 G1
             n_aff = 0;
-            if ((double)entries >= 24.0e6 * scale) {
+            if ((double)entries >= 24.0e6 * scale && entries < ((size_t)1 << 31)) {   // map words keep bit 31 for the pair flag
                 double avg = (double)entries / (double)K;   // a level needs lists of >= 4 entries on average
                 double pairs = (double)entries * 0.5;
                 while (n_aff < 8 && avg >= 4.0 && pairs > 6.0e6 * scale) {
@@ -453,6 +498,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
                 }
             }
         }
+        if (entries >= ((size_t)1 << 31)) n_aff = 0;   // (also when the level count was forced by option)
         const size_t CBy = ops->coord_bytes;
         const uint32_t m = (uint32_t)c->opt.msm_pair_m, m2 = (uint32_t)c->opt.msm_pair_m2;
         size_t Eb = entries;
@@ -467,19 +513,23 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
         }
         for (int lvl = 0; lvl < n_aff; lvl++) {
             const size_t Eout = (Eb + (K < Eb ? K : Eb)) / 2 + 1;      // bound on the outputs of this level
-            const size_t nT = (Eout + m - 1) / m, nU = (nT + m2 - 1) / m2;
+            const size_t nT = 32 * ((Eout + 32 * (size_t)m - 1) / (32 * (size_t)m)), nU = (nT + m2 - 1) / m2;   // chains (pair_chains)
             uint32_t* aoff = c->ws[p ? WS_AOFF_B : WS_AOFF_A].as<uint32_t>(K + 1);
             uint32_t* alen = c->ws[p ? WS_ALEN_B : WS_ALEN_A].as<uint32_t>(K + 1);
             char* pt = (char*)c->ws[p ? WS_PT_B : WS_PT_A].get(Eout * 2 * CBy);
             char* pre = (char*)c->ws[WS_PRE].get(Eout * CBy);
             char* Tt = (char*)c->ws[WS_T].get((nT + 1) * CBy);
             char* pre2 = (char*)c->ws[WS_PRE2].get((nT + 1) * CBy);
+            uint32_t* pmap = c->ws[WS_PAIRMAP].as<uint32_t>(Eout);
             ZKM_LAUNCH(k_pair_lens, kblocks, 256, 0, s, cur_off, K, alen);
             exclusive_scan(c, alen, aoff, K + 1, s);
-            ops->pair_fwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt,
-                          c->opt.msm_prefetch_fwd, lvl == 0 ? xarr : nullptr);
+            {
+                const uint64_t need = Eout / (256 * ZKM_MAP_M) + 1;
+                ZKM_LAUNCH(k_pair_map, (unsigned)(need < grid_stream ? need : grid_stream), 256, 0, s, cur_off, aoff, K, pmap);
+            }
+            ops->pair_fwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, pmap, aoff, K, m, pre, Tt, lvl == 0 ? xarr : nullptr);
             ops->pair_inv((unsigned)c->sm_count, nU, s, aoff, K, m, m2, Tt, pre2);
-            ops->pair_bwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, cur_off, aoff, K, m, pre, Tt, pt, c->opt.msm_prefetch_bwd);
+            ops->pair_bwd((unsigned)c->sm_count, nT, s, lvl == 0, cur_src, cur_idx, pmap, aoff, K, m, pre, Tt, pt);
             if (n_cnt_levels < 8) cnt_words[4 + n_cnt_levels++] = aoff + K;   // outputs of this level
             cur_off = aoff;
             cur_cnt = alen;

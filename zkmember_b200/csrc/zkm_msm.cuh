@@ -57,16 +57,15 @@ struct CurveOps {
     // batched-affine pairwise level (zkm_msm_affine.cuh): denominators + prefix products, inversion of the
     // per-thread totals, unwind + affine additions into the next level's array
     void (*pair_fwd)(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                     const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, int pf,
-                     const void* xarr);
+                     const uint32_t* map, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, const void* xarr);
     // level-0 x-coordinate array (xarr_slot bytes per base; 0 = this group does not use one)
     void (*build_xarr)(unsigned sm_count, cudaStream_t s, const void* bases, uint64_t n, void* xarr);
     int xarr_slot;
     void (*pair_inv)(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
                      uint32_t m2, void* T, void* pre2);
     void (*pair_bwd)(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                     const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
-                     void* dst, int pf);
+                     const uint32_t* map, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
+                     void* dst);
     size_t coord_bytes;
 };
 
@@ -80,9 +79,11 @@ inline uint32_t msm_reduce_group(uint32_t B, uint32_t W) {
 // XYZZ records needed by CurveOps::reduce for `contrib`
 inline size_t msm_contrib_records(int W, uint32_t B) {
     uint32_t per_w = B / msm_reduce_group(B, (uint32_t)W);
-    // acc + slice sums (quad path: 256 per slice) + run + the upper levels of the hierarchical reduction (each at most
-    // 1/4 of the level below, acc and run) + 16 per-level window sums
-    return 2 * (size_t)W * per_w + (size_t)W * ((per_w + 255) / 256) + (size_t)W * (per_w + 64) + 16 * (size_t)W + 16;
+    // quad path: acc + slice sums (256 per slice).  Hierarchical path: acc + run of level 0, the upper levels (each at
+    // most 1/4 of the level below + 1 per window, acc and run: < per_w + 64), 17 per-level window sums, slice sums of the
+    // plain sums (one per 256 records of every level, rounded up per level and window: < per_w / 128 + 34)
+    return 2 * (size_t)W * per_w + (size_t)W * ((per_w + 255) / 256) + (size_t)W * (per_w + 64) + 17 * (size_t)W +
+           (size_t)W * (per_w / 128 + 34) + 16;
 }
 
 const CurveOps* ops_g1_bls();

@@ -49,26 +49,15 @@ __device__ __forceinline__ const char* pair_src(const char* src, const uint32_t*
     return src + (size_t)i * (2 * CB);
 }
 
-// Level 0 gathers whole base records at random: ask L2 for the records a few pairs ahead of the one being
-// worked on (no registers held, unlike a software pipeline), so the dependent-product chain of the thread
-// finds them in L2 instead of waiting out a DRAM round trip.  `bytes` = 48/96/... rounded up to 32-byte sectors.
-__device__ __forceinline__ void prefetch_l2(const char* p, int bytes) {
-    for (int o = 0; o < bytes; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-}
-
-struct PairCursor {  // bucket of the current output element
-    uint32_t k, lo, hi;
-};
-__device__ __forceinline__ void cursor_seek(PairCursor& c, const uint32_t* __restrict__ off_out, uint32_t K, uint32_t e) {
-    uint32_t a = 0, b = K;  // off_out[a] <= e < off_out[b]
-    while (b - a > 1) {
-        uint32_t mid = (a + b) >> 1;
-        if (off_out[mid] <= e) a = mid; else b = mid;
-    }
-    c.k = a;
-    c.lo = off_out[a];
-    c.hi = off_out[a + 1];
-}
+// Work distribution of a level (round 2): the E outputs are cut into blocks of 32 m consecutive outputs, one block per
+// WARP; lane l of the warp owns the chain of outputs l, l + 32, l + 64, ... of the block (m of them).  Consecutive
+// lanes therefore touch consecutive outputs at every step: the map words, the prefix products, the outputs and -- from
+// level 1 on -- the inputs are read and written as contiguous 32-element runs.  (Round 1 gave every thread m
+// CONSECUTIVE outputs: each warp-wide access touched 32 different lines 6 KB apart; the forward pass of levels >= 1 ran
+// at 2.2 TB/s and the unwind pass lost 27 % of its stall cycles to memory.)  Montgomery's trick does not care which
+// elements share a chain.  Where output e finds its inputs is precomputed per level by k_pair_map (zkm_msm.cu):
+// map[e] = first input position | (two inputs ? 1 << 31 : 0).
+__device__ __forceinline__ uint32_t pair_chains(uint32_t E, uint32_t m) { return 32u * ((E + 32u * m - 1u) / (32u * m)); }
 
 // classification of one output element
 struct PairKind {
@@ -94,40 +83,25 @@ __global__ void __launch_bounds__(256) k_build_xarr(const char* __restrict__ bas
 
 template <class F, bool L0>
 __global__ void __launch_bounds__(256)
-k_pair_fwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off_in,
-           const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, char* __restrict__ pre, char* __restrict__ T, int pf,
+k_pair_fwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ map,
+           const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, char* __restrict__ pre, char* __restrict__ T,
            const char* __restrict__ xarr) {
     constexpr int CB = CoordIO<F>::BYTES;
     constexpr int XS = XArr<F>::SLOT > 0 ? XArr<F>::SLOT : 2 * CB;
     const uint32_t E = off_out[K];
-    uint32_t Ein = 0;
-    if (L0) Ein = off_in[K];
     const bool use_x = L0 && XArr<F>::SLOT > 0 && xarr != nullptr;
-    const uint32_t nT = (E + m - 1) / m;
+    const uint32_t nT = pair_chains(E, m);
+    const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nT; t += gridDim.x * blockDim.x) {
-        const uint32_t e0 = t * m, e1 = (e0 + m < E) ? e0 + m : E;
-        PairCursor c;
-        cursor_seek(c, off_out, K, e0);
-        uint32_t ib = off_in[c.k], ie = off_in[c.k + 1];
+        const uint32_t e0 = (t >> 5) * 32u * m + lane;
         F run = F::one();
-        for (uint32_t e = e0; e < e1; e++) {
-            while (e >= c.hi) {
-                c.k++;
-                c.lo = c.hi;
-                c.hi = off_out[c.k + 1];
-                ib = ie;
-                ie = off_in[c.k + 1];
-            }
-            const uint32_t i0 = ib + 2 * (e - c.lo);
-            if (L0 && pf > 0) {   // x coordinates of the pair `pf` outputs ahead (list positions advance by ~2 per output)
-                const uint32_t pi = i0 + 2 * (uint32_t)pf;
-                if (pi + 1 < Ein) {
-                    prefetch_l2(src + (size_t)(idx[pi] & 0x7fffffffu) * (2 * CB), CB);
-                    prefetch_l2(src + (size_t)(idx[pi + 1] & 0x7fffffffu) * (2 * CB), CB);
-                }
-            }
+        for (uint32_t j = 0; j < m; j++) {
+            const uint32_t e = e0 + 32u * j;
+            if (e >= E) break;
+            const uint32_t mp = map[e];
             CoordIO<F>::st(pre + (size_t)e * CB, run);
-            if (i0 + 1 < ie) {
+            if (mp >> 31) {
+                const uint32_t i0 = mp & 0x7fffffffu;
                 uint32_t s0, s1;
                 const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
                 const char* p1 = pair_src<F, L0>(src, idx, i0 + 1, s1);
@@ -156,14 +130,14 @@ k_pair_fwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const
     }
 }
 
-// T[i] := 1 / T[i] for i < nT = ceil(E / m)
+// T[i] := 1 / T[i] for i < nT = pair_chains(E, m)
 template <class F>
 __global__ void __launch_bounds__(128)
 k_inv_batch(const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, uint32_t m2, char* __restrict__ T,
             char* __restrict__ pre2) {
     constexpr int CB = CoordIO<F>::BYTES;
     const uint32_t E = off_out[K];
-    const uint32_t nT = (E + m - 1) / m;
+    const uint32_t nT = pair_chains(E, m);
     const uint32_t nU = (nT + m2 - 1) / m2;
     for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nU; u += gridDim.x * blockDim.x) {
         const uint32_t i0 = u * m2, i1 = (i0 + m2 < nT) ? i0 + m2 : nT;
@@ -188,39 +162,30 @@ template <> struct PairBwdMinBlocks<Bw6_761_Fq> { static constexpr int value = 2
 
 template <class F, bool L0>
 __global__ void __launch_bounds__(128, PairBwdMinBlocks<F>::value)
-k_pair_bwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off_in,
+k_pair_bwd(const char* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ map,
            const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, const char* __restrict__ pre,
-           const char* __restrict__ Tinv, char* __restrict__ dst, int pf) {
+           const char* __restrict__ Tinv, char* __restrict__ dst) {
     constexpr int CB = CoordIO<F>::BYTES;
     const uint32_t E = off_out[K];
-    const uint32_t nT = (E + m - 1) / m;
+    const uint32_t nT = pair_chains(E, m);
+    const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nT; t += gridDim.x * blockDim.x) {
-        const uint32_t e0 = t * m, e1 = (e0 + m < E) ? e0 + m : E;
-        PairCursor c;
-        cursor_seek(c, off_out, K, e1 - 1);
-        uint32_t ib = off_in[c.k], ie = off_in[c.k + 1];
+        const uint32_t e0 = (t >> 5) * 32u * m + lane;
+        if (e0 >= E) continue;
+        uint32_t cnt = (E - e0 + 31u) >> 5;     // outputs of this chain
+        if (cnt > m) cnt = m;
         F run = CoordIO<F>::ld_plain(Tinv + (size_t)t * CB);
-        for (uint32_t e = e1; e-- > e0;) {
-            while (e < c.lo) {
-                c.k--;
-                c.hi = c.lo;
-                c.lo = off_out[c.k];
-                ie = ib;
-                ib = off_in[c.k];
-            }
-            const uint32_t i0 = ib + 2 * (e - c.lo);
-            if (L0 && pf > 0 && i0 >= 2 * (uint32_t)pf) {   // the walk is backwards: whole records (x, y) of an earlier pair
-                const uint32_t pi = i0 - 2 * (uint32_t)pf;
-                prefetch_l2(src + (size_t)(idx[pi] & 0x7fffffffu) * (2 * CB), 2 * CB);
-                prefetch_l2(src + (size_t)(idx[pi + 1] & 0x7fffffffu) * (2 * CB), 2 * CB);
-            }
+        for (uint32_t j = cnt; j-- > 0;) {
+            const uint32_t e = e0 + 32u * j;
+            const uint32_t mp = map[e];
+            const uint32_t i0 = mp & 0x7fffffffu;
             uint32_t s0, s1;
             const char* p0 = pair_src<F, L0>(src, idx, i0, s0);
             F x0 = L0 ? CoordIO<F>::ld_gather(p0) : CoordIO<F>::ld_plain(p0);
             F y0 = L0 ? CoordIO<F>::ld_gather(p0 + CB) : CoordIO<F>::ld_plain(p0 + CB);
             if (s0) y0 = neg(y0);
             F x3 = x0, y3 = y0;
-            if (i0 + 1 < ie) {
+            if (mp >> 31) {
                 const char* p1 = pair_src<F, L0>(src, idx, i0 + 1, s1);
                 F x1 = L0 ? CoordIO<F>::ld_gather(p1) : CoordIO<F>::ld_plain(p1);
                 F y1 = L0 ? CoordIO<F>::ld_gather(p1 + CB) : CoordIO<F>::ld_plain(p1 + CB);

@@ -248,32 +248,6 @@ __global__ void __launch_bounds__(128) k_window_combine(const XYZZ<F>* __restric
     if (q == 0) st_xyzz(wsum + w, v);
 }
 
-// out[w * nslices + slice] = sum of in[w * per_w + slice * chunk ... + chunk)   (block = 64 threads)
-template <class F>
-__global__ void __launch_bounds__(64) k_window_sum(const XYZZ<F>* __restrict__ in, uint32_t per_w, uint32_t chunk,
-                                                   uint32_t nslices, XYZZ<F>* __restrict__ out) {
-    __shared__ XYZZ<F> sh[64];
-    const uint32_t w = blockIdx.x / nslices, slice = blockIdx.x % nslices;
-    const uint32_t begin = slice * chunk;
-    const uint32_t end = begin + chunk < per_w ? begin + chunk : per_w;
-    XYZZ<F> acc = XYZZ<F>::identity();
-    for (uint32_t t = begin + threadIdx.x; t < end; t += 64) {
-        XYZZ<F> q = ld_xyzz(in + (size_t)w * per_w + t);
-        add_sel(acc, q);
-    }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 32; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            XYZZ<F> a = sh[threadIdx.x], b = sh[threadIdx.x + s];
-            xyzz_add_ni(a, b);
-            sh[threadIdx.x] = a;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) st_xyzz(out + blockIdx.x, sh[0]);
-}
-
 // result record: x, y (Montgomery affine), then one u64 flag: 0 = finite point, 1 = point at infinity (x = 0, y = 1
 // like ark-ec GroupAffine::zero()), 2 = INVALID: a scalar of the MSM was not canonical (bits at or above the modulus
 // width) -- the host entry points turn it into ZKM_ERR_SCALAR_RANGE, the *_device ones document it (zkm_b200.h)
@@ -370,40 +344,79 @@ __global__ void __launch_bounds__(128) k_window_sum_quad(const XYZZ<F>* __restri
     if (threadIdx.x == 0) st_xyzz(out + blockIdx.x, sh[0]);
 }
 
-// Plain sums of the acc arrays of ALL upper levels of the hierarchical reduction in one launch: block (w, level)
-// sums acc_level[w * per .. + per) -> sums[(level + 1) * W + w].  (One k_window_sum_quad launch per level ran them one
-// after another: seven serial ~165 us tree sums at 2^24.)
-struct LevelSums {
-    int n;                 // upper levels
-    uint32_t off[16];      // record offset of the level's acc array inside `upper`
-    uint32_t per[16];      // chunks per window at that level
+// Plain sums of the acc arrays of ALL levels of the hierarchical reduction (level 0: W x per_w records, the upper
+// levels a quarter of the one below each) in two launches: stage 1, one CTA per slice of <= 256 records (32 quads: 8
+// dependent additions + a 5-step tree); stage 2, one CTA per (level, window) over its <= 32 slice sums.  ~170 us at
+// 2^24 / c = 20; round 2a summed level 0 with a two-step single-lane tree (0.50 ms) and every upper level with one
+// 32-quad CTA per window (64 dependent additions on the largest level: 0.71 ms).
+constexpr uint32_t ZKM_SUM_SLICE = 256;
+struct SumJobs {
+    int n;                  // levels
+    uint32_t off[17];       // record offset of the level's acc array from `base`
+    uint32_t per[17];       // records per window at that level
+    uint32_t nsl[17];       // slices per window
+    uint32_t cta0[18];      // first stage-1 CTA of the level (cta0[n] = total)
+    uint32_t sl0[17];       // first slice-sum record of the level
 };
+// sh[0] = sum of the 32 quads' partial sums (one CTA of 128 threads).  Written out on the shared array itself and after
+// every address has been computed: the same tree behind a helper taking the array as a pointer, with the destination
+// index read from the parameter struct after the calls, returned wrong points on sm_100a / nvcc 12.9 (caught by
+// tools/microbench/sums_check.cu against a serial sum; the bisection variants are in that file).
+#define ZKM_CTA_TREE_SUM_QUAD(sh, acc, quad, q, mask)                    \
+    do {                                                                 \
+        if ((q) == 0) (sh)[quad] = (acc);                                \
+        __syncthreads();                                                 \
+        for (uint32_t s2_ = 16; s2_ > 0; s2_ >>= 1) {                    \
+            if ((quad) < s2_) {                                          \
+                XYZZ<F> a_ = (sh)[quad], b_ = (sh)[(quad) + s2_];        \
+                xyzz_add_quad(a_, b_, q, mask);                          \
+                if ((q) == 0) (sh)[quad] = a_;                           \
+            }                                                            \
+            __syncthreads();                                             \
+        }                                                                \
+    } while (0)
 template <class F>
-__global__ void __launch_bounds__(128) k_level_sums_quad(const XYZZ<F>* __restrict__ upper, LevelSums ls, uint32_t W,
-                                                         XYZZ<F>* __restrict__ sums) {
+__global__ void __launch_bounds__(128) k_sums_stage1(const XYZZ<F>* __restrict__ base, SumJobs jb, uint32_t W,
+                                                     XYZZ<F>* __restrict__ slice_sums) {
     __shared__ XYZZ<F> sh[32];
-    const uint32_t w = blockIdx.x % W, lvl = blockIdx.x / W;
-    const uint32_t per = ls.per[lvl];
-    const XYZZ<F>* in = upper + ls.off[lvl] + (size_t)w * per;
+    int L = 0;
+    while (L + 1 < jb.n && blockIdx.x >= jb.cta0[L + 1]) L++;
+    const uint32_t r = blockIdx.x - jb.cta0[L];
+    const uint32_t w = r / jb.nsl[L], sl = r % jb.nsl[L];
+    const uint32_t per = jb.per[L];
+    const XYZZ<F>* in = base + jb.off[L] + (size_t)w * per;
+    XYZZ<F>* dst = slice_sums + jb.sl0[L] + (size_t)w * jb.nsl[L] + sl;
+    const uint32_t lo = sl * ZKM_SUM_SLICE, hi = lo + ZKM_SUM_SLICE < per ? lo + ZKM_SUM_SLICE : per;
     const int q = threadIdx.x & 3;
     const uint32_t quad = threadIdx.x >> 2;
     const uint32_t mask = 0xfu << (threadIdx.x & 28);
     XYZZ<F> acc = XYZZ<F>::identity();
-    for (uint32_t t = quad; t < per; t += 32) {
+    for (uint32_t t = lo + quad; t < hi; t += 32) {
         XYZZ<F> v = ld_xyzz(in + t);
         xyzz_add_quad(acc, v, q, mask);
     }
-    if (q == 0) sh[quad] = acc;
-    __syncthreads();
-    for (uint32_t s = 16; s > 0; s >>= 1) {
-        if (quad < s) {
-            XYZZ<F> a = sh[quad], b = sh[quad + s];
-            xyzz_add_quad(a, b, q, mask);
-            if (q == 0) sh[quad] = a;
-        }
-        __syncthreads();
+    ZKM_CTA_TREE_SUM_QUAD(sh, acc, quad, q, mask);
+    if (threadIdx.x == 0) st_xyzz(dst, sh[0]);
+}
+// block (level, w): sums[level * W + w] = sum of the level's slice sums of window w
+template <class F>
+__global__ void __launch_bounds__(128) k_sums_stage2(const XYZZ<F>* __restrict__ slice_sums, SumJobs jb, uint32_t W,
+                                                     XYZZ<F>* __restrict__ sums) {
+    __shared__ XYZZ<F> sh[32];
+    const uint32_t w = blockIdx.x % W, L = blockIdx.x / W;
+    const uint32_t nsl = jb.nsl[L];
+    const XYZZ<F>* in = slice_sums + jb.sl0[L] + (size_t)w * nsl;
+    XYZZ<F>* dst = sums + (size_t)L * W + w;
+    const int q = threadIdx.x & 3;
+    const uint32_t quad = threadIdx.x >> 2;
+    const uint32_t mask = 0xfu << (threadIdx.x & 28);
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t t = quad; t < nsl; t += 32) {
+        XYZZ<F> v = ld_xyzz(in + t);
+        xyzz_add_quad(acc, v, q, mask);
     }
-    if (threadIdx.x == 0) st_xyzz(sums + (size_t)(lvl + 1) * W + w, sh[0]);
+    ZKM_CTA_TREE_SUM_QUAD(sh, acc, quad, q, mask);
+    if (threadIdx.x == 0) st_xyzz(dst, sh[0]);
 }
 
 // ---- fold: a bucket whose list was cut into several tasks holds several partial sums, consecutive records
@@ -581,13 +594,12 @@ template <class G> struct PairOpsProvider { static constexpr bool external = fal
 template <> struct PairOpsProvider<G1Bw6> { static constexpr bool external = true; };
 template <> struct PairOpsProvider<G2Bw6> { static constexpr bool external = true; };
 void bw6_pair_fwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                  const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, int pf,
-                  const void* xarr);
+                  const uint32_t* map, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, const void* xarr);
 void bw6_pair_inv(unsigned sm_count, uint64_t nU_bound, cudaStream_t s, const uint32_t* off_out, uint32_t K, uint32_t m,
                   uint32_t m2, void* T, void* pre2);
 void bw6_pair_bwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                  const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
-                  void* dst, int pf);
+                  const uint32_t* map, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
+                  void* dst);
 void bw6_build_xarr(unsigned sm_count, cudaStream_t s, const void* bases, uint64_t n, void* xarr);
 
 template <class G>
@@ -626,15 +638,14 @@ struct OpsImpl {
         return (unsigned)(need < cap ? (need ? need : 1) : cap);
     }
     static void pair_fwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                         const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, int pf,
-                         const void* xarr) {
+                         const uint32_t* map, const uint32_t* off_out, uint32_t K, uint32_t m, void* pre, void* T, const void* xarr) {
         static std::atomic<int> occ0{0}, occ1{0};
         if (level0) {
             unsigned grid = pair_grid(k_pair_fwd<F, true>, 256, sm_count, nT_bound, &occ0);
-            ZKM_LAUNCH((k_pair_fwd<F, true>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T, pf, (const char*)xarr);
+            ZKM_LAUNCH((k_pair_fwd<F, true>), grid, 256, 0, s, (const char*)src, idx, map, off_out, K, m, (char*)pre, (char*)T, (const char*)xarr);
         } else {
             unsigned grid = pair_grid(k_pair_fwd<F, false>, 256, sm_count, nT_bound, &occ1);
-            ZKM_LAUNCH((k_pair_fwd<F, false>), grid, 256, 0, s, (const char*)src, idx, off_in, off_out, K, m, (char*)pre, (char*)T, pf, (const char*)xarr);
+            ZKM_LAUNCH((k_pair_fwd<F, false>), grid, 256, 0, s, (const char*)src, idx, map, off_out, K, m, (char*)pre, (char*)T, (const char*)xarr);
         }
     }
     // x coordinates of `n` bases in 64-byte slots (level-0 forward gathers); a no-op for fields without such a layout
@@ -650,15 +661,15 @@ struct OpsImpl {
         ZKM_LAUNCH(k_inv_batch<F>, grid, 128, 0, s, off_out, K, m, m2, (char*)T, (char*)pre2);
     }
     static void pair_bwd(unsigned sm_count, uint64_t nT_bound, cudaStream_t s, int level0, const void* src, const uint32_t* idx,
-                         const uint32_t* off_in, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre,
-                         const void* Tinv, void* dst, int pf) {
+                         const uint32_t* map, const uint32_t* off_out, uint32_t K, uint32_t m, const void* pre, const void* Tinv,
+                         void* dst) {
         static std::atomic<int> occ0{0}, occ1{0};
         if (level0) {
             unsigned grid = pair_grid(k_pair_bwd<F, true>, 128, sm_count, nT_bound, &occ0);
-            ZKM_LAUNCH((k_pair_bwd<F, true>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst, pf);
+            ZKM_LAUNCH((k_pair_bwd<F, true>), grid, 128, 0, s, (const char*)src, idx, map, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst);
         } else {
             unsigned grid = pair_grid(k_pair_bwd<F, false>, 128, sm_count, nT_bound, &occ1);
-            ZKM_LAUNCH((k_pair_bwd<F, false>), grid, 128, 0, s, (const char*)src, idx, off_in, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst, pf);
+            ZKM_LAUNCH((k_pair_bwd<F, false>), grid, 128, 0, s, (const char*)src, idx, map, off_out, K, m, (const char*)pre, (const char*)Tinv, (char*)dst);
         }
     }
     static void reduce(cudaStream_t s, const void* items, const uint32_t* off, const uint32_t* cnt, MsmPlan pl,
@@ -686,9 +697,8 @@ struct OpsImpl {
             // chunk) and run (plain chunk sum).  The chunk offsets t * g are worth g * sum_t t * run_t: the same
             // reduction over the run sums (a dense array now, four lanes per chain), and so on until one chunk is left.
             XYZZ<F>* acc0 = (XYZZ<F>*)contrib;                       // RW * per_w
-            XYZZ<F>* stage2 = acc0 + (size_t)RW * per_w;             // slice sums of the level-0 window sum
-            XYZZ<F>* run0 = stage2 + (size_t)RW * ((per_w + 1023) / 1024) + 1;
-            XYZZ<F>* upper = run0 + (size_t)RW * per_w;              // acc / run of the upper levels
+            XYZZ<F>* run0 = acc0 + (size_t)RW * per_w;
+            XYZZ<F>* upper = run0 + (size_t)RW * per_w;              // acc / run of the upper levels, sums, slice sums
             unsigned rblocks = (RW * per_w + 127) / 128;
             ZKM_LAUNCH((k_bucket_reduce<F, true>), rblocks, 128, 0, s, (const XYZZ<F>*)items, off, cnt, RW, pl.B, g, acc0, run0);
             ReduceLevels lv;
@@ -696,22 +706,24 @@ struct OpsImpl {
             lv.lg[0] = 31 - __builtin_clz(g);
             size_t used = 0;                                           // records of `upper` in use
             auto take = [&](size_t n) { XYZZ<F>* p = upper + used; used += n; return p; };
-            XYZZ<F>* sums = take((size_t)16 * RW);
-            // plain sum of the level-0 acc array: two-step tree per window
-            {
-                uint32_t nslices = (per_w + 1023) / 1024;
-                if (nslices > 1) {
-                    uint32_t chunk = (per_w + nslices - 1) / nslices;
-                    ZKM_LAUNCH(k_window_sum<F>, RW * nslices, 64, 0, s, (const XYZZ<F>*)acc0, per_w, chunk, nslices, stage2);
-                    ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)stage2, nslices, nslices, 1u, sums);
-                } else {
-                    ZKM_LAUNCH(k_window_sum<F>, RW, 64, 0, s, (const XYZZ<F>*)acc0, per_w, per_w, 1u, sums);
-                }
-            }
+            XYZZ<F>* sums = take((size_t)17 * RW);
+            SumJobs jb;
+            jb.n = 0;
+            uint32_t n_cta = 0, n_sl = 0;
+            auto add_level = [&](const XYZZ<F>* acc, uint32_t per) {
+                const int L = jb.n++;
+                jb.off[L] = (uint32_t)(acc - acc0);
+                jb.per[L] = per;
+                jb.nsl[L] = (per + ZKM_SUM_SLICE - 1) / ZKM_SUM_SLICE;
+                jb.cta0[L] = n_cta;
+                jb.sl0[L] = n_sl;
+                n_cta += RW * jb.nsl[L];
+                n_sl += RW * jb.nsl[L];
+                jb.cta0[L + 1] = n_cta;
+            };
+            add_level(acc0, per_w);
             const XYZZ<F>* cur_run = run0;
             uint32_t cur_per = per_w;
-            LevelSums lsum;
-            lsum.n = 0;
             while (cur_per > 1) {
                 const uint32_t Bp = cur_per - 1;                      // chunk t >= 1 has weight t: bucket b = t - 1
                 // upper levels are pure latency (2 gk dependent additions each, little parallel work): short chunks.
@@ -723,15 +735,15 @@ struct OpsImpl {
                 XYZZ<F>* runk = take((size_t)RW * per2);
                 ZKM_LAUNCH(k_reduce_dense_quad<F>, (RW * per2 * 4 + 127) / 128, 128, 0, s, cur_run, cur_per, 1u, Bp, gk, per2, RW,
                            acck, runk);
-                lsum.off[lsum.n] = (uint32_t)(acck - upper);
-                lsum.per[lsum.n] = per2;
-                lsum.n++;
+                add_level(acck, per2);
                 lv.lg[lv.n] = 31 - __builtin_clz(gk);
                 lv.n++;
                 cur_run = runk;
                 cur_per = per2;
             }
-            if (lsum.n) ZKM_LAUNCH(k_level_sums_quad<F>, RW * lsum.n, 128, 0, s, (const XYZZ<F>*)upper, lsum, RW, sums);
+            XYZZ<F>* slice_sums = take(n_sl);
+            ZKM_LAUNCH(k_sums_stage1<F>, n_cta, 128, 0, s, (const XYZZ<F>*)acc0, jb, RW, slice_sums);
+            ZKM_LAUNCH(k_sums_stage2<F>, RW * (unsigned)jb.n, 128, 0, s, (const XYZZ<F>*)slice_sums, jb, RW, sums);
             ZKM_LAUNCH(k_window_combine<F>, (RW * 4 + 127) / 128, 128, 0, s, (const XYZZ<F>*)sums, lv, RW, (XYZZ<F>*)wsum);
         }
         ZKM_LAUNCH(k_msm_final<F>, 1, 32, 0, s, (const XYZZ<F>*)wsum, pl.RW, pl.c, flags, d_out);
