@@ -543,8 +543,8 @@ def main():
     proxy = None
     if not args.skip_proxy:
         torch.cuda.synchronize()
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "180",
-               "--inflight", "6", "--device", str(local_rank)]
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "groth16_proxy.py"), "--log-n", "16", "--proofs", "160",
+               "--inflight", "4", "--device", str(local_rank)]
         if world > 1:
             cmd += ["--host-wait", "2"]      # replicas share the host's cores: block instead of spinning on the read-back
         if rank == 0 and world == 1 and not args.skip_cpu:

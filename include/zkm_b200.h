@@ -35,8 +35,9 @@
  *
  * Device-pointer entry points (`*_device`): pointers must be 16-byte aligned (128-bit vector accesses) and must
  * belong to an initialised device -- the call runs on the device that owns the OUTPUT pointer.  `stream` is a
- * cudaStream_t of that device; NULL means a library-owned NON-BLOCKING stream, which does NOT synchronise with the
- * legacy default stream: the producers of the inputs must have completed (or pass the stream they run on).
+ * cudaStream_t of that device; NULL means the library's own NON-BLOCKING stream of that device (one per device: NULL-stream
+ * calls are ordered among themselves), which does NOT synchronise with the legacy default stream or with the caller's
+ * streams: producers of the inputs that ran elsewhere must have completed (or pass the stream they run on).
  *
  * Ownership: the caller owns every buffer it passes; the library reads inputs / writes outputs
  * during the call only and retains nothing except bases registered with zkm_bases_register* (and, for

@@ -35,7 +35,7 @@ names = [launches[i]["name"] for i in ids]
 fin = [k for k, n in enumerate(names) if "k_msm_final" in n]
 lo, hi = fin[-2] + 1, fin[-1] + 1
 short = lambda n: n.split("(")[0].replace("void ", "").replace("zkm::", "")
-acc_kernels = ("k_pair_fwd", "k_pair_bwd", "k_inv_batch", "k_accum_affine", "k_build_xarr")
+acc_kernels = ("k_pair_fwd", "k_pair_bwd", "k_inv_batch", "k_accum_affine", "k_build_xarr", "k_pair_map", "k_pair_lens")
 per = collections.OrderedDict()
 msm_total = msm_ms = acc_total = acc_ms = 0.0
 for k in range(lo, hi):

@@ -95,28 +95,38 @@ int device_count_initialised() {
 //      calls: no new dependency, no new memory -- the sequential caller stays on one lane);
 //   2. the lowest lane whose previous work has finished;
 //   3. otherwise the free lanes in turn (the call then waits for that lane's previous work on the GPU).
-static Context* pick_free_lane(int dev, cudaStream_t hint) {
+static Context* pick_free_lane(int dev, cudaStream_t hint, uint64_t key = 0) {
     static unsigned cursor[64] = {0};
     auto& v = g->lanes[dev];
     const size_t L = v.size();
     if (hint)
         for (Context* c : v)
             if (!c->busy && c->last_stream == hint) return c;
+    // among the lanes whose previous work has finished: one that last served the same job (`key`: e.g. the same
+    // registered bases -> its workspaces already have the right sizes, no reallocation), else the lowest
     Context* pick = nullptr;
     for (Context* c : v) {
         if (c->busy) continue;
         if (!c->done_ev || cudaEventQuery(c->done_ev) == cudaSuccess) {
-            pick = c;
-            break;
+            if (key && c->affinity == key) {
+                pick = c;
+                break;
+            }
+            if (!pick) pick = c;
+            if (!key) break;
         }
     }
     cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
-    if (pick) return pick;
+    if (pick) {
+        pick->affinity = key;
+        return pick;
+    }
     unsigned& cur = cursor[dev & 63];
     for (size_t k = 0; k < L; k++) {
         Context* c = v[(cur + k) % L];
         if (!c->busy) {
             cur = (unsigned)((cur + k + 1) % L);
+            c->affinity = key;
             return c;
         }
     }
@@ -139,7 +149,7 @@ Context* acquire_lane(int dev, cudaStream_t hint) {
     }
 }
 
-std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t hint0) {
+std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t hint0, const std::vector<uint64_t>* keys) {
     std::unique_lock<std::mutex> lk(g_lane_mu);
     if (!g || g->lanes.empty()) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
     std::vector<int> need(g->lanes.size(), 0);
@@ -158,7 +168,7 @@ std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t h
         if (ok) {
             std::vector<Context*> out;
             for (size_t i = 0; i < devs.size(); i++) {
-                Context* c = pick_free_lane(devs[i], i == 0 ? hint0 : nullptr);   // cannot fail: the free lanes were counted above
+                Context* c = pick_free_lane(devs[i], i == 0 ? hint0 : nullptr, keys && i < keys->size() ? (*keys)[i] : 0);   // cannot fail: the free lanes were counted above
                 c->busy = true;
                 c->opt = g->opt;
                 c->cur_stream = c->stream;
@@ -419,6 +429,13 @@ static int home_device_of(const void* dptr) {
     ZKM_FAIL(ZKM_ERR_ARG, "device pointer lives on CUDA device %d, which zkm_init* did not initialise", at.device);
 }
 
+// the stream a *_device call enqueues on: the caller's, or the device's library stream when the caller passed NULL
+static cudaStream_t call_stream(int dev, void* stream) {
+    if (stream) return (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(g_lane_mu);
+    return g->devs[dev]->null_stream;
+}
+
 // Device-resident MSMs over registrations, all ordered after the current point of `caller` and joined back into it.
 // Items whose registration is one part on the caller's device and that are alone in the call run directly on the
 // caller's stream.  Otherwise every job gets its own host thread, lane and stream (concurrent on the GPU: the five MSMs
@@ -447,12 +464,16 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
     const bool fast = items.size() == 1 && flat.size() == 1 && flat[0].job.part->dev == home;
     // lane 0: the home lane; lanes 1..: one per job -- all taken together (no hold-and-wait between concurrent calls)
     std::vector<int> devs{home};
+    std::vector<uint64_t> keys{0};     // lane affinity: the part of the registration a job runs over (same workspace sizes)
     if (!fast)
-        for (const Flat& f : flat) devs.push_back(f.job.part->dev);
-    MultiLaneGuard lanes(devs, caller_or_null);
+        for (const Flat& f : flat) {
+            devs.push_back(f.job.part->dev);
+            keys.push_back((uint64_t)(uintptr_t)f.job.part);
+        }
+    MultiLaneGuard lanes(devs, caller_or_null, &keys);
     Context* hc = lanes.c[0];
     ZKM_CUDA(cudaSetDevice(hc->device));
-    cudaStream_t caller = caller_or_null ? caller_or_null : hc->stream;
+    cudaStream_t caller = caller_or_null;
     StreamScope hscope(hc, caller);
     // fast path: one job on the caller's device -> no threads, no events, the caller's stream itself
     if (fast) {
@@ -747,6 +768,7 @@ static int32_t init_devices(const int32_t* devices, int32_t count) {
                     ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
                     c->cur_stream = c->stream;
                 }
+                ZKM_CUDA(cudaStreamCreateWithFlags(&sh->null_stream, cudaStreamNonBlocking));
                 // workspaces come from the default memory pool (DevBuf): keep freed blocks in the process
                 cudaMemPool_t pool;
                 ZKM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -778,7 +800,10 @@ static int32_t init_devices(const int32_t* devices, int32_t count) {
             ZKM_CUDA(cudaSetDevice(want[0]));
         } catch (...) {
             for (auto& v : ng->lanes) free_lanes(v);
-            for (Shared* sh : ng->devs) delete sh;
+            for (Shared* sh : ng->devs) {
+                if (sh->null_stream) cudaStreamDestroy(sh->null_stream);
+                delete sh;
+            }
             delete ng;
             throw;
         }
@@ -845,6 +870,7 @@ void zkm_shutdown(void) {
     for (Shared* sh : og->devs) {
         cudaSetDevice(sh->device);
         ntt_release_tables(sh);
+        if (sh->null_stream) cudaStreamDestroy(sh->null_stream);
         delete sh;
     }
     delete og;
@@ -1083,7 +1109,8 @@ int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t
     return guarded([&] {
         if (!d_out || (n && !d_scalars)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
         std::vector<DevItem> items{DevItem{lookup(handle, offset, n), offset, n, d_scalars, d_out}};
-        msm_items_device(items, home_device_of(d_out), (cudaStream_t)stream);
+        const int home = home_device_of(d_out);
+        msm_items_device(items, home, call_stream(home, stream));
     });
 }
 
@@ -1103,7 +1130,8 @@ int32_t zkm_msm_batch_registered_device(int32_t count, const uint64_t* handles, 
             if (!d_outs[i] || (n[i] && !d_scalars[i])) ZKM_FAIL(ZKM_ERR_ARG, "item %d: null device pointer", i);
             items.push_back(DevItem{lookup(handles[i], offsets[i], n[i]), offsets[i], n[i], d_scalars[i], d_outs[i]});
         }
-        msm_items_device(items, home_device_of(d_outs[0]), (cudaStream_t)stream);
+        const int home = home_device_of(d_outs[0]);
+        msm_items_device(items, home, call_stream(home, stream));
     });
 }
 
@@ -1112,10 +1140,12 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
     return guarded([&] {
         check_curve_group(curve, group);
         if (!d_out || (m && !d_points)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(home_device_of(d_out), (cudaStream_t)stream);
+        const int home = home_device_of(d_out);
+        cudaStream_t s = call_stream(home, stream);
+        LaneGuard lane(home, s);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
-        points_sum_run(c, curve, group, d_points, m, d_out, stream ? (cudaStream_t)stream : c->stream);
+        points_sum_run(c, curve, group, d_points, m, d_out, s);
     });
 }
 
@@ -1144,10 +1174,11 @@ int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uin
                        int32_t coset, void* stream) {
     return guarded([&] {
         if (!d_in || !d_out) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(home_device_of(d_out), (cudaStream_t)stream);
+        const int home = home_device_of(d_out);
+        cudaStream_t s = call_stream(home, stream);
+        LaneGuard lane(home, s);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
-        cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
         StreamScope scope(c, s);
         ntt_run(c, curve, d_in, d_out, log_n, inverse != 0, coset != 0, s);
     });
@@ -1156,10 +1187,12 @@ int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uin
 int32_t zkm_fr_into_repr_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, size_t n, void* stream) {
     return guarded([&] {
         if (n && (!d_in || !d_out)) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(n ? home_device_of(d_out) : 0, (cudaStream_t)stream);
+        const int home = n ? home_device_of(d_out) : 0;
+        cudaStream_t s = call_stream(home, stream);
+        LaneGuard lane(home, s);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
-        fr_into_repr_run(c, curve, d_in, d_out, (uint64_t)n, stream ? (cudaStream_t)stream : c->stream);
+        fr_into_repr_run(c, curve, d_in, d_out, (uint64_t)n, s);
     });
 }
 
@@ -1167,10 +1200,11 @@ int32_t zkm_witness_map_device(int32_t curve, uint64_t* d_a, uint64_t* d_b, uint
                                void* stream) {
     return guarded([&] {
         if (!d_a || !d_b || !d_c || !d_h) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(home_device_of(d_h), (cudaStream_t)stream);
+        const int home = home_device_of(d_h);
+        cudaStream_t s = call_stream(home, stream);
+        LaneGuard lane(home, s);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
-        cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
         StreamScope scope(c, s);
         witness_map_run(c, curve, d_a, d_b, d_c, log_n, d_h, s);
     });
@@ -1339,10 +1373,12 @@ int32_t zkm_testgen_progression_device(int32_t curve, int32_t group, uint64_t a0
     return guarded([&] {
         check_curve_group(curve, group);
         if (n && !d_bases_xy) ZKM_FAIL(ZKM_ERR_ARG, "null device pointer");
-        LaneGuard lane(n ? home_device_of(d_bases_xy) : 0);
+        const int home = n ? home_device_of(d_bases_xy) : 0;
+        cudaStream_t s = call_stream(home, stream);
+        LaneGuard lane(home, s);
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
-        testgen_progression(c, curve, group, a0, d, n, d_bases_xy, stream ? (cudaStream_t)stream : c->stream);
+        testgen_progression(c, curve, group, a0, d, n, d_bases_xy, s);
     });
 }
 

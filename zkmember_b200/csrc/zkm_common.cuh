@@ -153,6 +153,9 @@ struct Shared {
     int device = -1;                       // CUDA ordinal
     int index = 0;                         // position in the initialised device list
     int sm_count = 148;
+    // The stream behind `stream == NULL` of the *_device entry points: ONE library-owned non-blocking stream per device,
+    // so that successive NULL-stream calls stay ordered among themselves whichever lanes they borrow.
+    cudaStream_t null_stream = nullptr;
     std::mutex tw_mu;                      // guards `twiddles`
     std::map<uint64_t, void*> twiddles;    // key -> device table (twiddles, coset powers, domain constants)
 };
@@ -193,6 +196,7 @@ struct Context {
     // every call orders itself after `done_ev` and re-records it when it has enqueued its work.
     cudaEvent_t done_ev = nullptr;
     cudaStream_t last_stream = nullptr;   // stream of the lane's previous call (lane selection: see pick_free_lane)
+    uint64_t affinity = 0;                // job key of the lane's previous call (same key -> same workspace sizes)
     cudaEvent_t sync_ev = nullptr;   // blocking-sync event for host waits while many lanes are busy
     cudaEvent_t spin_ev = nullptr;   // spinning event for the fold-depth read-back
     void begin(cudaStream_t s) {
@@ -241,10 +245,12 @@ struct LaneGuard {
 
 // Several lanes at once, all or nothing: a call that needs a lane per job never holds some while waiting for others,
 // so concurrent multi-lane calls cannot deadlock each other.  devs[i] = device index of lane i.
-std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t hint0 = nullptr);   // hint0: for devs[0]
+std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t hint0 = nullptr,
+                                    const std::vector<uint64_t>* keys = nullptr);   // hint0: for devs[0]; keys[i]: affinity of lane i
 struct MultiLaneGuard {
     std::vector<Context*> c;
-    explicit MultiLaneGuard(const std::vector<int>& devs, cudaStream_t hint0 = nullptr) : c(acquire_lanes(devs, hint0)) {}
+    explicit MultiLaneGuard(const std::vector<int>& devs, cudaStream_t hint0 = nullptr, const std::vector<uint64_t>* keys = nullptr)
+        : c(acquire_lanes(devs, hint0, keys)) {}
     ~MultiLaneGuard() { for (Context* x : c) release_lane(x); }
     MultiLaneGuard(const MultiLaneGuard&) = delete;
     MultiLaneGuard& operator=(const MultiLaneGuard&) = delete;

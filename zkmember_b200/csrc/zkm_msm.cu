@@ -34,26 +34,43 @@ namespace zkm {
 // for window w_only: one launch per window keeps the write set (n x 4 B) inside the 126 MB L2, so the
 // random 4-byte stores merge into full sectors before they reach HBM.
 // SL = 32-bit limbs per scalar: 8 (BigInteger256) or 12 (BigInteger384, BW6-761).
-// (Warp-aggregated atomics -- __match_any_sync on the bucket key -- were measured in round 2 and dropped: same-address
-// atomics are cheap on B200 (a 45 %-ones witness sorts as fast as uniform scalars, profiles/sweep_msm_*_witness_r2l.jsonl),
-// while the match doubled the cost of every window it ran on: sort 5.3 -> 7.0 ms at 2^24 on all windows, 6.1 ms on two.)
+// Bucket atomics.  Same-address atomics serialise: window 0 of a Groth16 witness is 45 % ones (7.5 M hits on one counter
+// at 2^24: sort 4.1 -> 8.2 ms), the top window has few real bits, a registration with window multiples has ONE small
+// bucket set for all windows.  On those windows the lanes that share the bucket of the warp's first entry are counted
+// with one atomic (two ballots and a shuffle).  A full __match_any_sync on every window was measured and dropped: it
+// doubled the cost of each window it ran on (sort 5.3 -> 7.0 ms at 2^24 uniform).
+// `dig` (MODE 0, large MSMs): the histogram pass also writes every digit as one word, dig[w * n + i] = |d| | sign << 31
+// (0: no entry), so that the per-window scatter launches (k_msm_scatter_row) read 4 bytes per scalar instead of
+// decoding the whole 32-byte scalar again in each of the W launches (13 x 512 MB at 2^24 -> 0.9 GB written + read).
 template <int MODE, int SL>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
                                                     uint64_t n, MsmPlan pl, int w_only,
                                                     uint32_t* __restrict__ counts_or_cursor,
-                                                    uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (inf && inf[i]) continue;
-        const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * SL);
+                                                    uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags,
+                                                    uint32_t* __restrict__ dig) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool write_dig = MODE == 0 && dig != nullptr;
+    // warp-uniform loop: the lanes of a warp walk the digit loop together (lanes without a scalar carry zeros)
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
+        const bool in_range = i < n;
+        bool live = in_range && !(inf && inf[i]);
         uint32_t s[SL];
         uint32_t any = 0;
 #pragma unroll
-        for (int v = 0; v < SL / 4; v++) {
-            uint4 a = __ldg(sp + v);
-            s[4 * v] = a.x; s[4 * v + 1] = a.y; s[4 * v + 2] = a.z; s[4 * v + 3] = a.w;
-            any |= a.x | a.y | a.z | a.w;
+        for (int v = 0; v < SL; v++) s[v] = 0;
+        if (live) {
+            const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * SL);
+#pragma unroll
+            for (int v = 0; v < SL / 4; v++) {
+                uint4 a = __ldg(sp + v);
+                s[4 * v] = a.x; s[4 * v + 1] = a.y; s[4 * v + 2] = a.z; s[4 * v + 3] = a.w;
+                any |= a.x | a.y | a.z | a.w;
+            }
         }
-        if (any == 0) continue;
+        live = live && any != 0;
+        if (!write_dig && __ballot_sync(0xffffffffu, live) == 0) continue;   // (with `dig` the zero rows must still be written)
         const uint32_t mask = (1u << pl.c) - 1u;
         uint64_t buf = 0;
         int nb = 0, w = 0;
@@ -77,13 +94,33 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                     sign = 1;
                     carry = 1;
                 }
-                if (d != 0 && (MODE == 0 || w_only < 0 || w == w_only)) {
-                    uint32_t key = (uint32_t)w * pl.key_stride + (d - 1);
-                    if (MODE == 0) {
-                        atomicAdd(&counts_or_cursor[key], 1u);
-                    } else {
-                        uint32_t pos = atomicAdd(&counts_or_cursor[key], 1u);
-                        idx_out[pos] = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (sign << 31);
+                if (write_dig && in_range) dig[(size_t)w * n + i] = d ? (d | (sign << 31)) : 0u;
+                if (MODE == 0 || w_only < 0 || w == w_only) {      // uniform over the warp
+                    const bool hit = d != 0;                        // (lanes without a scalar have d == 0)
+                    const uint32_t key = (uint32_t)w * pl.key_stride + (d - 1);
+                    const uint32_t entry = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (sign << 31);
+                    if (w == 0 || w == pl.W - 1 || pl.key_stride == 0) {
+                        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                        if (hits) {
+                            const int l0 = __ffs(hits) - 1;
+                            const uint32_t k0 = __shfl_sync(0xffffffffu, key, l0);
+                            const uint32_t same = __ballot_sync(0xffffffffu, hit && key == k0);
+                            uint32_t base = 0;
+                            if ((int)lane == l0) base = atomicAdd(&counts_or_cursor[k0], (uint32_t)__popc(same));
+                            if (MODE == 1) base = __shfl_sync(0xffffffffu, base, l0);
+                            if (hit) {
+                                if (key == k0) {
+                                    if (MODE == 1) idx_out[base + (uint32_t)__popc(same & lt_mask)] = entry;
+                                } else if (MODE == 0) {
+                                    atomicAdd(&counts_or_cursor[key], 1u);
+                                } else {
+                                    idx_out[atomicAdd(&counts_or_cursor[key], 1u)] = entry;
+                                }
+                            }
+                        }
+                    } else if (hit) {
+                        if (MODE == 0) atomicAdd(&counts_or_cursor[key], 1u);
+                        else idx_out[atomicAdd(&counts_or_cursor[key], 1u)] = entry;
                     }
                 }
                 w++;
@@ -91,7 +128,36 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
         }
         // a canonical scalar is < r < 2^scalar_bits: any bit at or above that position (or a digit carry out of the
         // top window) marks the input as non-canonical -> flag word 2 of the result record / ZKM_ERR_SCALAR_RANGE
-        if (MODE == 0 && (buf != 0 || carry != 0 || (s[SL - 1] >> (pl.scalar_bits & 31)) != 0)) atomicOr(&flags[1], 1u);
+        if (MODE == 0 && live && (buf != 0 || carry != 0 || (s[SL - 1] >> (pl.scalar_bits & 31)) != 0)) atomicOr(&flags[1], 1u);
+    }
+}
+
+// scatter of one window from its row of digit words (see k_msm_digits): idx_out[cursor[key]++] = entry.
+// The lanes that share the bucket of the warp's first entry take their slots with ONE atomic (two ballots and a shuffle,
+// not a __match_any_sync): skewed rows -- window 0 of a Groth16 witness is 45 % ones, the top window has few real bits --
+// otherwise serialise millions of returning atomics on one counter (2^24 witness scalars: sort 4.1 -> 11.2 ms without it),
+// and uniform rows pay almost nothing.
+__global__ void __launch_bounds__(256) k_msm_scatter_row(const uint32_t* __restrict__ dig_row, uint64_t n, MsmPlan pl, int w,
+                                                         uint32_t* __restrict__ cursor, uint32_t* __restrict__ idx_out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
+        const uint32_t dw = i < n ? __ldg(dig_row + i) : 0u;
+        const bool hit = dw != 0;
+        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+        if (hits == 0) continue;
+        const uint32_t key = (uint32_t)w * pl.key_stride + ((dw & 0x7fffffffu) - 1u);
+        const int l0 = __ffs(hits) - 1;
+        const uint32_t k0 = __shfl_sync(0xffffffffu, key, l0);
+        const uint32_t same = __ballot_sync(0xffffffffu, hit && key == k0);
+        uint32_t base = 0;
+        if ((int)lane == l0) base = atomicAdd(&cursor[k0], (uint32_t)__popc(same));
+        base = __shfl_sync(0xffffffffu, base, l0);
+        if (hit) {
+            const uint32_t pos = key == k0 ? base + (uint32_t)__popc(same & lt_mask) : atomicAdd(&cursor[key], 1u);
+            idx_out[pos] = ((uint32_t)w * pl.idx_stride + pl.idx_base + (uint32_t)i) | (dw & 0x80000000u);
+        }
     }
 }
 
@@ -329,7 +395,7 @@ static const CurveOps* curve_ops(int curve, int group) {
 enum WsSlot {
     WS_COUNTS = 0, WS_OFF, WS_CURSOR, WS_IDX, WS_TPB_A, WS_TBASE_A, WS_FOLDLIST, WS_FOLDSEG, WS_TSTART, WS_TLEN,
     WS_ORDER, WS_LENHIST, WS_LENCUR, WS_PART_A, WS_FOLDSTAGE, WS_CONTRIB, WS_WSUM, WS_FLAGS, WS_CUBTMP,
-    WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2, WS_XARR, WS_PAIRMAP
+    WS_AOFF_A, WS_AOFF_B, WS_ALEN_A, WS_ALEN_B, WS_PT_A, WS_PT_B, WS_PRE, WS_T, WS_PRE2, WS_XARR, WS_PAIRMAP, WS_DIGITS
 };
 
 static void exclusive_scan(Context* c, const uint32_t* in, uint32_t* out, size_t count, cudaStream_t s) {
@@ -440,31 +506,28 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     ZKM_CUDA(cudaMemsetAsync(counts, 0, (K + 1) * sizeof(uint32_t), s));
     ZKM_CUDA(cudaMemsetAsync(flags, 0, 8 * sizeof(uint32_t), s));
     const bool wide = fr_words(curve) == 6;   // 377-bit scalars (BW6-761)
+    // all windows scattered by one launch when the whole list array fits in L2; otherwise one launch per window
+    // (write set n x 4 B inside L2), fed from the digit words the histogram pass leaves behind
+    const bool one_scatter = entries * sizeof(uint32_t) <= (96u << 20);
+    uint32_t* dig = one_scatter ? nullptr : c->ws[WS_DIGITS].as<uint32_t>(entries);
     if (wide)
         ZKM_LAUNCH((k_msm_digits<0, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
-                   (uint32_t*)nullptr, flags);
+                   (uint32_t*)nullptr, flags, dig);
     else
         ZKM_LAUNCH((k_msm_digits<0, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
-                   (uint32_t*)nullptr, flags);
+                   (uint32_t*)nullptr, flags, dig);
     exclusive_scan(c, counts, off, K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(cursor, off, K * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    if (entries * sizeof(uint32_t) <= (96u << 20)) {
-        // the whole list array fits in L2: one launch scatters every window
+    if (one_scatter) {
         if (wide)
             ZKM_LAUNCH((k_msm_digits<1, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1,
-                       cursor, idx, flags);
+                       cursor, idx, flags, (uint32_t*)nullptr);
         else
             ZKM_LAUNCH((k_msm_digits<1, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1,
-                       cursor, idx, flags);
+                       cursor, idx, flags, (uint32_t*)nullptr);
     } else {
-        for (int w = 0; w < pl.W; w++) {
-            if (wide)
-                ZKM_LAUNCH((k_msm_digits<1, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w,
-                           cursor, idx, flags);
-            else
-                ZKM_LAUNCH((k_msm_digits<1, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, w,
-                           cursor, idx, flags);
-        }
+        for (int w = 0; w < pl.W; w++)
+            ZKM_LAUNCH(k_msm_scatter_row, grid_stream, 256, 0, s, (const uint32_t*)(dig + (size_t)w * n), (uint64_t)n, pl, w, cursor, idx);
     }
 
     mark(1);
