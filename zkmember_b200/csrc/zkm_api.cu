@@ -269,7 +269,7 @@ static std::shared_ptr<BasesReg> build_registration(int curve, int group, const 
         p.ordinal = c->device;
         ZKM_CUDA(cudaSetDevice(c->device));
         const size_t bytes = p.n * rec;
-        ZKM_CUDA(cudaMalloc(&p.d_xy, bytes ? bytes : 16));
+        ZKM_CUDA(malloc_retry((void**)&p.d_xy, bytes ? bytes : 16));
         reg->bytes += bytes;
         // cudaMemcpyDefault: `xy` may be a host pointer or a device pointer on any device (UVA picks the route)
         if (bytes) ZKM_CUDA(cudaMemcpyAsync(p.d_xy, (const char*)xy + p.first * rec, bytes, cudaMemcpyDefault, c->stream));
@@ -871,6 +871,7 @@ void zkm_shutdown(void) {
         cudaSetDevice(sh->device);
         ntt_release_tables(sh);
         if (sh->null_stream) cudaStreamDestroy(sh->null_stream);
+        DevBuf::trim_pool();     // the lanes' workspaces went back to the default pool: return them to the device
         delete sh;
     }
     delete og;

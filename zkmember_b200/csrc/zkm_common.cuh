@@ -65,7 +65,19 @@ struct DevBuf {
             p = nullptr;
             cap = 0;
             size_t want = bytes + (bytes >> 3) + 256;
-            ZKM_CUDA(cudaMallocAsync(&p, want, s));
+            cudaError_t e = cudaMallocAsync(&p, want, s);
+            if (e == cudaErrorMemoryAllocation) {
+                // the pool keeps freed blocks (fragmentation, blocks still owed to other streams): hand everything that is
+                // really free back to the device and try once more before reporting ZKM_ERR_OOM
+                cudaGetLastError();
+                p = nullptr;
+                trim_pool();
+                e = cudaMallocAsync(&p, want, s);
+            }
+            if (e != cudaSuccess) {
+                p = nullptr;
+                ZKM_CUDA(e);
+            }
             cap = want;
         }
         return p;
@@ -77,7 +89,27 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
+    // synchronise the current device and release the unused memory of its default pool
+    static void trim_pool() {
+        int dev = 0;
+        cudaMemPool_t pool;
+        cudaDeviceSynchronize();
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        cudaGetLastError();
+    }
 };
+
+// cudaMalloc for the long-lived allocations (registered bases, tables): if the device is full because the default pool is
+// holding freed workspace blocks, trim the pool and try once more
+inline cudaError_t malloc_retry(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        DevBuf::trim_pool();
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
 
 struct PinnedBuf {
     void* p = nullptr;

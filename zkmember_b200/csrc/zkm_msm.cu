@@ -416,7 +416,7 @@ void msm_precompute(Context* c, int curve, int group, BasesPart* part, cudaStrea
     int W = windows_for(ops->scalar_bits, cb);
     if ((double)part->n * W >= 2.0e9) ZKM_FAIL(ZKM_ERR_ARG, "precomputed table of %zu x %d points exceeds 2^31 entries", part->n, W);
     const size_t rec = 2 * (size_t)coord_words(curve, group) * 8;
-    ZKM_CUDA(cudaMalloc(&part->d_table, part->n * (size_t)W * rec));
+    ZKM_CUDA(malloc_retry((void**)&part->d_table, part->n * (size_t)W * rec));
     ops->precompute(s, part->d_xy, part->d_inf, (uint64_t)part->n, cb, W, part->d_table);
     part->pre_c = cb;
     part->pre_W = W;

@@ -506,7 +506,7 @@ static const uint32_t* get_twiddles(Context* c, int curve, int k, int inverse, c
     if (it != c->twiddles.end()) return (const uint32_t*)it->second;
     uint64_t count = 1ull << (k - 1);
     void* p = nullptr;
-    ZKM_CUDA(cudaMalloc(&p, count * P::N * 4));
+    ZKM_CUDA(malloc_retry((void**)&p, count * P::N * 4));
     c->twiddles[key] = p;
     unsigned blocks = (unsigned)((count + 255) / 256);
     ZKM_LAUNCH(k_gen_twiddles<P>, blocks, 256, 0, s, (uint32_t*)p, k, inverse, count);
@@ -527,7 +527,7 @@ static const uint32_t* get_tw4(Context* c, int curve, int kk, int R, int inverse
     auto it = c->twiddles.find(key);
     if (it != c->twiddles.end()) return (const uint32_t*)it->second;
     void* p = nullptr;
-    ZKM_CUDA(cudaMalloc(&p, bytes));
+    ZKM_CUDA(malloc_retry((void**)&p, bytes));
     c->twiddles[key] = p;
     ZKM_LAUNCH(k_gen_tw4<P>, (unsigned)(((1ull << kk) + 255) / 256), 256, 0, s, (uint32_t*)p, kk, R, inverse);
     ZKM_CUDA(cudaStreamSynchronize(s));
@@ -549,9 +549,9 @@ static void get_coset(Context* c, int curve, int k, int inverse, cudaStream_t s,
         return;
     }
     void *pl = nullptr, *ph = nullptr;
-    ZKM_CUDA(cudaMalloc(&pl, nlo * P::N * 4));
+    ZKM_CUDA(malloc_retry((void**)&pl, nlo * P::N * 4));
     c->twiddles[klo] = pl;
-    ZKM_CUDA(cudaMalloc(&ph, nhi * P::N * 4));
+    ZKM_CUDA(malloc_retry((void**)&ph, nhi * P::N * 4));
     c->twiddles[khi] = ph;
     unsigned blocks = (unsigned)((nlo + nhi + 255) / 256);
     ZKM_LAUNCH(k_gen_coset<P>, blocks, 256, 0, s, (uint32_t*)pl, (uint32_t*)ph, nlo, nhi, inverse, k);
@@ -655,7 +655,7 @@ static void ntt_run_t(Context* c, int curve, const uint64_t* d_in, uint64_t* d_o
         auto it = c->twiddles.find(key);
         void* p;
         if (it == c->twiddles.end()) {
-            ZKM_CUDA(cudaMalloc(&p, 5 * P::N * 4));
+            ZKM_CUDA(malloc_retry((void**)&p, 5 * P::N * 4));
             c->twiddles[key] = p;
             ZKM_LAUNCH(k_domain_constants<P>, 1, 32, 0, s, (uint32_t*)p, k);
             ZKM_CUDA(cudaStreamSynchronize(s));
@@ -705,7 +705,7 @@ static void witness_map_t(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, u
         uint64_t key = table_key(VANISH, curve, (int)log_n, 0);
         auto it = c->twiddles.find(key);
         if (it == c->twiddles.end()) {
-            ZKM_CUDA(cudaMalloc(&zinv, P::N * 4));
+            ZKM_CUDA(malloc_retry((void**)&zinv, P::N * 4));
             c->twiddles[key] = zinv;
             ZKM_LAUNCH(k_vanishing_inv<P>, 1, 32, 0, s, (uint32_t*)zinv, (int)log_n);
             ZKM_CUDA(cudaStreamSynchronize(s));
