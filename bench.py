@@ -530,8 +530,11 @@ def main():
                             "algorithmic": "64 B/element (read once + write once)", "traffic": ntt_traffic},
                "int_pipe": {"achieved": ntt_gmads, "peak": IMAD_PEAK_GMADS, "unit": "GMAD/s",
                             "frac": ntt_gmads / IMAD_PEAK_GMADS,
-                            "algorithmic": "log2(n)/2 Fr products per element x 136 wide MADs (executed: + the four-step and "
-                                           "coset products, ~1 per element per extra pass)",
+                            "algorithmic": "log2(n)/2 Fr products per element x 136 wide MADs, the nominal 2 N^2 + N of an 8-limb "
+                                           "Montgomery product (executed: + the four-step and coset products, ~1 per element per "
+                                           "extra pass; BLS12-381 Fr issues 120 per product: its reduction limbs p_0 = 1 and "
+                                           "p_1 = 2^32 - 1 need no multiplication)",
+                            "executed_mads_per_product": 120 if CURVE_NAME == "bls12_381" else 136,
                             "peak_source": "measured: %s (profiles/int_pipe_peak_r2.jsonl)" % IMAD_PEAK_SRC},
                "note": "device-resident, out of place; integer-pipe bound on B200 (see DESIGN.md): the HBM fraction "
                        "is reported as the contract asks, int_pipe is the binding roofline"}
