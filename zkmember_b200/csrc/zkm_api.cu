@@ -102,20 +102,28 @@ static Context* pick_free_lane(int dev, cudaStream_t hint, uint64_t key = 0) {
     if (hint)
         for (Context* c : v)
             if (!c->busy && c->last_stream == hint) return c;
-    // among the lanes whose previous work has finished: one that last served the same job (`key`: e.g. the same
-    // registered bases -> its workspaces already have the right sizes, no reallocation), else the lowest
+    // among the lanes whose previous work has finished: one that last served the same job (`key`: the same registered
+    // bases and size class -> its workspaces already have the right sizes, no reallocation), else the lowest
+    auto idle = [](Context* c) { return !c->done_ev || cudaEventQuery(c->done_ev) == cudaSuccess; };
     Context* pick = nullptr;
-    for (Context* c : v) {
-        if (c->busy) continue;
-        if (!c->done_ev || cudaEventQuery(c->done_ev) == cudaSuccess) {
-            if (key && c->affinity == key) {
+    if (key)
+        for (Context* c : v)
+            if (!c->busy && c->affinity == key && idle(c)) {
                 pick = c;
                 break;
             }
-            if (!pick) pick = c;
-            if (!key) break;
-        }
-    }
+    if (!pick && key)       // a lane nobody has a claim on, before taking over one that serves another job
+        for (Context* c : v)
+            if (!c->busy && c->affinity == 0 && idle(c)) {
+                pick = c;
+                break;
+            }
+    if (!pick)
+        for (Context* c : v)
+            if (!c->busy && idle(c)) {
+                pick = c;
+                break;
+            }
     cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
     if (pick) {
         pick->affinity = key;
@@ -133,13 +141,13 @@ static Context* pick_free_lane(int dev, cudaStream_t hint, uint64_t key = 0) {
     return nullptr;
 }
 
-Context* acquire_lane(int dev, cudaStream_t hint) {
+Context* acquire_lane(int dev, cudaStream_t hint, uint64_t key) {
     std::unique_lock<std::mutex> lk(g_lane_mu);
     if (!g || g->lanes.empty()) ZKM_FAIL(ZKM_ERR_NOT_INIT, "zkm_init() has not been called (or failed)");
     if (dev < 0 || dev >= (int)g->lanes.size()) ZKM_FAIL(ZKM_ERR_ARG, "device index %d out of range (%zu initialised)", dev, g->lanes.size());
     for (;;) {
         if (!g) ZKM_FAIL(ZKM_ERR_NOT_INIT, "library was shut down");
-        if (Context* c = pick_free_lane(dev, hint)) {
+        if (Context* c = pick_free_lane(dev, hint, key)) {
             c->busy = true;
             c->opt = g->opt;      // snapshot: stable for the whole call whatever zkm_set_option does meanwhile
             c->cur_stream = c->stream;
@@ -320,6 +328,13 @@ static std::vector<Job> split_jobs(const BasesReg& r, size_t offset, size_t n) {
     return jobs;
 }
 
+// lane affinity of an MSM job: the registered part it runs over and the size class of the run (workspaces are sized by both)
+static uint64_t lane_key(const BasesPart* p, size_t n) {
+    int lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    return ((uint64_t)(uintptr_t)p) ^ ((uint64_t)(lg + 1) << 56);
+}
+
 static void run_part(Context* c, const BasesReg& r, const Job& j, const uint64_t* d_scal, uint64_t* d_rec, cudaStream_t s) {
     const size_t rec = 2 * (size_t)coord_words(r.curve, r.group) * 8;
     const BasesPart& p = *j.part;
@@ -355,7 +370,7 @@ static void msm_reg_host(const std::shared_ptr<BasesReg>& reg, size_t offset, co
         *out_inf = rec_flag(h[2 * W]);
     };
     if (jobs.size() <= 1) {
-        LaneGuard lane(jobs.empty() ? 0 : jobs[0].part->dev);
+        LaneGuard lane(jobs.empty() ? 0 : jobs[0].part->dev, nullptr, jobs.empty() ? 0 : lane_key(jobs[0].part, jobs[0].count));
         Context* c = lane.c;
         ZKM_CUDA(cudaSetDevice(c->device));
         StreamScope scope(c, c->stream);
@@ -468,7 +483,7 @@ static void msm_items_device(std::vector<DevItem>& items, int home, cudaStream_t
     if (!fast)
         for (const Flat& f : flat) {
             devs.push_back(f.job.part->dev);
-            keys.push_back((uint64_t)(uintptr_t)f.job.part);
+            keys.push_back(lane_key(f.job.part, f.job.count));
         }
     MultiLaneGuard lanes(devs, caller_or_null, &keys);
     Context* hc = lanes.c[0];

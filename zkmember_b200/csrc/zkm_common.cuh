@@ -263,13 +263,13 @@ struct StreamScope {
 constexpr int ZKM_NUM_LANES = 48;
 // blocks until a lane of device index `dev` is free; throws ZKM_ERR_NOT_INIT before zkm_init.  `hint`: the stream the
 // call is going to enqueue on, if it is the caller's (a lane last used on that stream is preferred)
-Context* acquire_lane(int dev = 0, cudaStream_t hint = nullptr);
+Context* acquire_lane(int dev = 0, cudaStream_t hint = nullptr, uint64_t key = 0);   // key: lane affinity (see pick_free_lane)
 void release_lane(Context* c);
 int busy_lane_count();
 int device_count_initialised();
 struct LaneGuard {
     Context* c;
-    explicit LaneGuard(int dev = 0, cudaStream_t hint = nullptr) : c(acquire_lane(dev, hint)) {}
+    explicit LaneGuard(int dev = 0, cudaStream_t hint = nullptr, uint64_t key = 0) : c(acquire_lane(dev, hint, key)) {}
     ~LaneGuard() { release_lane(c); }
     LaneGuard(const LaneGuard&) = delete;
     LaneGuard& operator=(const LaneGuard&) = delete;

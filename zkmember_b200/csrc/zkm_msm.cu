@@ -622,7 +622,7 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     // cycles alone, 2.65 k with two warps per scheduler: tools/microbench/tail_latency.cu) and room on the SMs for the
     // kernels of concurrent MSMs (CTAs beyond the device-side task count exit at once).
     {
-        const size_t need = (T1max + 127) / 128, cap = (size_t)c->sm_count * 2;
+        const size_t need = (T1max + 127) / 128, cap = (size_t)c->sm_count * (size_t)ops->accum_ctas_per_sm;
         ops->accum_affine((unsigned)(need < cap ? need : cap), s, cur_src, cur_idx, TaskList{tstart, tlen, order, tbase, K}, part);
     }
     mark(4);

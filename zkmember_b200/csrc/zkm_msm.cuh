@@ -40,6 +40,7 @@ struct CurveOps {
     size_t xyzz_bytes;
     // K4: out[task] = sum of the (sign-adjusted) affine bases named by idx[...]
     void (*accum_affine)(unsigned grid, cudaStream_t s, const void* bases, const uint32_t* idx, TaskList tl, void* out);
+    int accum_ctas_per_sm;   // resident 128-thread CTAs of the accumulation kernel (register-bound)
     // fold: bucket k holds tpb[k] partial sums items[tbase[k] ..); afterwards its sum is items[tbase[k]].  fold_list,
     // seg_first, segtab, n_lists as written by k_tasks_count; `stage` holds one record per segment.
     void (*fold)(unsigned sm_count, cudaStream_t s, void* items, const uint32_t* tbase, const uint32_t* tpb,

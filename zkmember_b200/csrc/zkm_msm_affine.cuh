@@ -159,6 +159,9 @@ k_inv_batch(const uint32_t* __restrict__ off_out, uint32_t K, uint32_t m, uint32
 // field of BW6-761 keeps ~6 coordinates of 24 limbs live and gets 2 (<= 255 registers) instead of spilling.
 template <class F> struct PairBwdMinBlocks { static constexpr int value = 4; };
 template <> struct PairBwdMinBlocks<Bw6_761_Fq> { static constexpr int value = 2; };
+// round 2 (after the strided chains freed the cursor registers), measured at 2^24: 6 CTAs/SM for the 254-bit field (80 registers,
+// 32 bytes of stack) -2 % on the levels; 5 for the 381-bit field (96 registers, 128 bytes of stack) +3 % -- it stays at 4.
+template <> struct PairBwdMinBlocks<Bn254_Fq> { static constexpr int value = 6; };
 
 template <class F, bool L0>
 __global__ void __launch_bounds__(128, PairBwdMinBlocks<F>::value)

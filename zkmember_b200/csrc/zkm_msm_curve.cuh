@@ -86,8 +86,12 @@ template <class F>
 __device__ __noinline__ bool xyzz_to_affine_ni(const XYZZ<F>& p, F& x, F& y) { return xyzz_to_affine(p, x, y); }
 
 // ---------------------------------------------------------------------------------- K4 accumulation
+// CTAs per SM the accumulation kernel is compiled for: two (up to 255 registers).  Four (128 registers, 376 instead of 288
+// bytes of stack for the 381-bit field) was measured in round 2 and is SLOWER: accumulate 3.19 -> 3.64 ms at 2^21, 6.74 -> 7.22
+// at 2^20, 4.8 -> 5.0 at 2^24, no gain for concurrent small MSMs -- the extra spills sit on the dependent chain.
+template <class F> struct AccumMinBlocks { static constexpr int value = 2; };
 template <class F>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, AccumMinBlocks<F>::value)
 k_accum_affine(const char* __restrict__ bases, const uint32_t* __restrict__ idx, const TaskList tl, XYZZ<F>* __restrict__ out) {
     constexpr int CB = CoordIO<F>::BYTES;
     const uint32_t* __restrict__ tstart = tl.tstart;
@@ -770,6 +774,7 @@ struct OpsImpl {
         o.xyzz_bytes = sizeof(XYZZ<F>);
         o.accum_affine = accum_affine;
         o.fold = fold;
+        o.accum_ctas_per_sm = AccumMinBlocks<F>::value;
         o.reduce = reduce;
         o.write_identity = write_identity;
         o.points_sum = points_sum;
