@@ -191,8 +191,9 @@ int32_t zkm_ntt_device(int32_t curve, const uint64_t* d_in, uint64_t* d_out, uin
 /* d_out: 2 * W words (affine, Montgomery) followed by one u64 flag word: 0 = finite point, 1 = point at infinity,
  * 2 = INVALID -- a scalar had bits at or above the modulus width (what the host entry points report as
  * ZKM_ERR_SCALAR_RANGE; here the check happens on the device and the call has long returned).
- * Fully asynchronous: a fixed sequence of kernel launches on `stream`, no device read-back, no host wait -- the call
- * can be captured into a CUDA graph by the caller.  If the registration lives
+ * Fully asynchronous: a fixed sequence of kernel launches on `stream`, no device read-back, no host wait.  (Do not call it
+ * on a stream that is being CAPTURED into a CUDA graph: the library records its lane-completion events on `stream`.)  If the
+ * registration lives
  * on other devices (ZKM_REG_DEVICE / ZKM_REG_SHARD) the scalar slices and the result records cross NVLink with
  * peer copies and sharded partial sums are added on the caller's device. */
 int32_t zkm_msm_registered_device(uint64_t handle, size_t offset, const uint64_t* d_scalars, size_t n,
@@ -219,7 +220,7 @@ int32_t zkm_points_sum_device(int32_t curve, int32_t group, const uint64_t* d_po
  * set also store their window multiples 2^(c w) P -- W times the memory, one-time cost -- so that all
  * windows of later MSMs share one bucket set and the final doubling chain disappears; meant for proving
  * keys / SRS that are reused across many proofs), "msm_xarr" (0 | 1: level-0 x-coordinate array, default 1),
- * "msm_prefetch_fwd" / "msm_prefetch_bwd" (L2 prefetch distance of the level-0 gathers, default 0 = off),
+ * "msm_prefetch_fwd" / "msm_prefetch_bwd", "msm_fold" (round-1 knobs, accepted and ignored),
  * "msm_cache" (0 | 1 | 2) and "msm_cache_max_mb" (registration cache of zkm_msm_g1/g2, see there),
  * "spread_host_calls" (0 | 1: host-pointer zkm_ntt / zkm_witness_map calls rotate over the initialised devices),
  * "host_wait" (accepted and ignored: since round 2 an MSM has no device read-back to wait for).

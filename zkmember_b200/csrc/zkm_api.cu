@@ -188,15 +188,6 @@ std::vector<Context*> acquire_lanes(const std::vector<int>& devs, cudaStream_t h
     }
 }
 
-int busy_lane_count() {
-    std::lock_guard<std::mutex> lk(g_lane_mu);
-    int n = 0;
-    if (g)
-        for (auto& v : g->lanes)
-            for (Context* c : v) n += c->busy ? 1 : 0;
-    return n;
-}
-
 void release_lane(Context* c) {
     {
         std::lock_guard<std::mutex> lk(g_lane_mu);
@@ -721,8 +712,6 @@ static void free_lanes(std::vector<Context*>& lanes) {
         for (auto& e : c->pev)
             if (e) cudaEventDestroy(e);
         if (c->done_ev) cudaEventDestroy(c->done_ev);
-        if (c->sync_ev) cudaEventDestroy(c->sync_ev);
-        if (c->spin_ev) cudaEventDestroy(c->spin_ev);
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         delete c;

@@ -161,12 +161,11 @@ struct Options {
     int msm_precompute = 0;  // legacy switch: registrations made while set behave as if ZKM_REG_PRECOMPUTE was passed
     int msm_affine_levels = -1;  // batched-affine pairwise levels before the XYZZ tasks (-1 = automatic)
     int msm_pair_m = 64, msm_pair_m2 = 32;  // outputs per thread / totals per inversion thread in the pair levels
-    // L2 prefetch distance (pairs ahead) of the level-0 gathers; 0 = off.  Measured on B200 at 2^24: every setting
-    // > 0 is SLOWER (+10 ms each for fwd and bwd): the level-0 passes are bound by random-access DRAM throughput,
-    // not by latency, and the prefetches add traffic.  Kept as a knob, off by default.
+    // L2 prefetch distance of the level-0 gathers: measured SLOWER in round 1 (+10 ms each at 2^24: the passes are bound by
+    // random-access DRAM throughput, not latency); the prefetch code is gone, the options are accepted and ignored.
     int msm_prefetch_fwd = 0, msm_prefetch_bwd = 0;
     int msm_xarr = 1;            // level-0 forward pass gathers x from an array of 64-byte slots (48-byte coordinates)
-    int msm_fold = 0;            // fan-in of the XYZZ fold levels (0 = automatic: 4 for small MSMs, 16 for large)
+    int msm_fold = 0;            // (round 1: fan-in of the host-sized fold levels) accepted and ignored: see k_fold_*
     // zkm_msm_g1 / zkm_msm_g2 (the literal multi_scalar_mul(bases, scalars) signature): keep the uploaded bases as an
     // internal registration keyed by (host pointer, n, content fingerprint).  0 = off, 1 = fingerprint of 512 sampled
     // records (default: proving keys / SRS are immutable while a prover runs), 2 = fingerprint of every byte.
@@ -174,9 +173,7 @@ struct Options {
     int64_t msm_cache_max_mb = 32768;   // cached registrations are evicted least-recently-used above this
     int msm_cache_precompute = 1;       // cached vectors of <= 2^18 bases get window multiples when they come back
     int spread_host_calls = 0;   // host-pointer NTT / witness-map calls rotate over the initialised devices
-    // how a call waits for its one device read-back (fold depth): 0 = spin while <= 6 lanes of this process are busy, block
-    // otherwise; 1 = always spin; 2 = always block (several prover PROCESSES sharing the host's cores: spinning threads of
-    // one replica starve the launch threads of the others)
+    // (round 1: how a call waited for its one device read-back) accepted and ignored: an MSM has no read-back any more
     int host_wait = 0;
 };
 
@@ -229,8 +226,6 @@ struct Context {
     cudaEvent_t done_ev = nullptr;
     cudaStream_t last_stream = nullptr;   // stream of the lane's previous call (lane selection: see pick_free_lane)
     uint64_t affinity = 0;                // job key of the lane's previous call (same key -> same workspace sizes)
-    cudaEvent_t sync_ev = nullptr;   // blocking-sync event for host waits while many lanes are busy
-    cudaEvent_t spin_ev = nullptr;   // spinning event for the fold-depth read-back
     void begin(cudaStream_t s) {
         if (done_ev) ZKM_CUDA(cudaStreamWaitEvent(s, done_ev, 0));
         last_stream = s;
@@ -265,7 +260,6 @@ constexpr int ZKM_NUM_LANES = 48;
 // call is going to enqueue on, if it is the caller's (a lane last used on that stream is preferred)
 Context* acquire_lane(int dev = 0, cudaStream_t hint = nullptr, uint64_t key = 0);   // key: lane affinity (see pick_free_lane)
 void release_lane(Context* c);
-int busy_lane_count();
 int device_count_initialised();
 struct LaneGuard {
     Context* c;
