@@ -224,6 +224,7 @@ struct Context {
     // The lane's workspaces may still be in use by kernels enqueued on the stream of its previous borrower:
     // every call orders itself after `done_ev` and re-records it when it has enqueued its work.
     cudaEvent_t done_ev = nullptr;
+    cudaEvent_t feed_ev[9] = {nullptr};   // chunked scalar upload of the host entry points (see ScalarFeed); [8]: start marker
     cudaStream_t last_stream = nullptr;   // stream of the lane's previous call (lane selection: see pick_free_lane)
     uint64_t affinity = 0;                // job key of the lane's previous call (same key -> same workspace sizes)
     void begin(cudaStream_t s) {
@@ -304,8 +305,17 @@ void ntt_release_tables(Shared* sh);
 void fr_into_repr_run(Context* c, int curve, const uint64_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t stream);
 void witness_map_run(Context* c, int curve, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_n, uint64_t* d_h,
                      cudaStream_t stream);
+// Scalars that are still arriving in device memory: the caller copies them in `n` chunks on another stream, chunk i
+// (scalars [begin[i], begin[i + 1])) is complete when ev[i] has fired.  msm_run then runs its histogram pass chunk by chunk
+// behind the copies (everything after it needs all scalars).
+struct ScalarFeed {
+    int n = 0;
+    size_t begin[9] = {0};
+    cudaEvent_t ev[8] = {nullptr};
+};
 void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
-             size_t n, uint64_t* d_out, cudaStream_t stream, const BasesPart* pre = nullptr, size_t pre_offset = 0);
+             size_t n, uint64_t* d_out, cudaStream_t stream, const BasesPart* pre = nullptr, size_t pre_offset = 0,
+             const ScalarFeed* feed = nullptr);
 void msm_precompute(Context* c, int curve, int group, BasesPart* part, cudaStream_t stream);
 void kzg_quotient_run(Context* c, int curve, const uint64_t* d_coeffs, size_t n, const uint64_t* d_point, uint64_t* d_quot,
                       uint64_t* d_eval, cudaStream_t stream);

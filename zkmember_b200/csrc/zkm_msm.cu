@@ -47,14 +47,15 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
                                                     uint64_t n, MsmPlan pl, int w_only,
                                                     uint32_t* __restrict__ counts_or_cursor,
                                                     uint32_t* __restrict__ idx_out, uint32_t* __restrict__ flags,
-                                                    uint32_t* __restrict__ dig) {
+                                                    uint32_t* __restrict__ dig, uint64_t i_begin, uint64_t i_end) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const bool write_dig = MODE == 0 && dig != nullptr;
-    // warp-uniform loop: the lanes of a warp walk the digit loop together (lanes without a scalar carry zeros)
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+    // warp-uniform loop over the scalars [i_begin, i_end) (the whole array, or one chunk of a ScalarFeed): the lanes of a
+    // warp walk the digit loop together (lanes without a scalar carry zeros)
+    for (uint64_t i0 = i_begin + (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < i_end; i0 += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = i0 + lane;
-        const bool in_range = i < n;
+        const bool in_range = i < i_end;
         bool live = in_range && !(inf && inf[i]);
         uint32_t s[SL];
         uint32_t any = 0;
@@ -423,7 +424,7 @@ void msm_precompute(Context* c, int curve, int group, BasesPart* part, cudaStrea
 }
 
 void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_t* d_inf, const uint64_t* d_scalars,
-             size_t n, uint64_t* d_out, cudaStream_t s, const BasesPart* pre, size_t pre_offset) {
+             size_t n, uint64_t* d_out, cudaStream_t s, const BasesPart* pre, size_t pre_offset, const ScalarFeed* feed) {
     const CurveOps* ops = curve_ops(curve, group);
     if (n == 0) {
         ops->write_identity(s, d_out);
@@ -505,26 +506,75 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     const unsigned grid_stream = (unsigned)c->sm_count * 8;
     ZKM_CUDA(cudaMemsetAsync(counts, 0, (K + 1) * sizeof(uint32_t), s));
     ZKM_CUDA(cudaMemsetAsync(flags, 0, 8 * sizeof(uint32_t), s));
+    // ---- how many batched-affine levels this run takes (needed first: the x-coordinate array of level 0 depends only on
+    // the bases, so it is built BEFORE the histogram pass waits for the scalars -- behind a host upload it costs nothing)
+    int n_aff = c->opt.msm_affine_levels;
+    if (n_aff < 0) {
+        // Measured on B200 (profiles/experiment_affine_threshold_r1p.jsonl, BLS12-381 G1): a pairwise level costs
+        // ~0.33 ns per pair plus ~1 ms of fixed latency (inversion kernel, scans), the XYZZ accumulation it saves
+        // ~0.42 ns per entry -- so a level pays while it still has more than ~6 M pairs, and the whole scheme from
+        // ~24 M entries on (2^21 points: 18.9 -> 16.6 ms with two levels; 2^20: no gain).  Cheaper field products
+        // (BN254: 136 wide MADs instead of 300) raise both thresholds in proportion; they are NOT lowered for the
+        // heavier fields (G2, BW6-761), whose pair kernels run at 2 CTAs/SM and showed no gain below ~24 M entries
+        // (profiles/experiment_affine_rule_r1r.jsonl).
+        const double limbs = (double)ops->coord_bytes / 4.0 / (group == 2 && curve != ZKM_CURVE_BW6_761 ? 2.0 : 1.0);
+        const double mads = (2.0 * limbs * limbs + limbs) * (group == 2 && curve != ZKM_CURVE_BW6_761 ? 3.0 : 1.0);
+        const double scale = mads < 300.0 ? 300.0 / mads : 1.0;   // 1 for BLS12-381 G1
+        n_aff = 0;
+        if ((double)entries >= 24.0e6 * scale && entries < ((size_t)1 << 31)) {   // map words keep bit 31 for the pair flag
+            double avg = (double)entries / (double)K;   // a level needs lists of >= 4 entries on average
+            double pairs = (double)entries * 0.5;
+            while (n_aff < 8 && avg >= 4.0 && pairs > 6.0e6 * scale) {
+                avg *= 0.5;
+                pairs *= 0.5;
+                n_aff++;
+            }
+        }
+    }
+    if (entries >= ((size_t)1 << 31)) n_aff = 0;   // (also when the level count was forced by option)
+    // x coordinates of the bases in 64-byte slots for the level-0 forward gathers (one DRAM burst per x);
+    // rebuilt per call (2.5 GB of streaming traffic at 2^24, ~0.4 ms) -- not for tables of window multiples
+    const void* xarr = nullptr;
+    if (n_aff > 0 && ops->xarr_slot > 0 && !use_pre && c->opt.msm_xarr) {
+        void* xa = c->ws[WS_XARR].get(n * (size_t)ops->xarr_slot);
+        ops->build_xarr((unsigned)c->sm_count, s, d_bases, (uint64_t)n, xa);
+        xarr = xa;
+    }
     const bool wide = fr_words(curve) == 6;   // 377-bit scalars (BW6-761)
     // all windows scattered by one launch when the whole list array fits in L2; otherwise one launch per window
     // (write set n x 4 B inside L2), fed from the digit words the histogram pass leaves behind
     const bool one_scatter = entries * sizeof(uint32_t) <= (96u << 20);
     uint32_t* dig = one_scatter ? nullptr : c->ws[WS_DIGITS].as<uint32_t>(entries);
-    if (wide)
-        ZKM_LAUNCH((k_msm_digits<0, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
-                   (uint32_t*)nullptr, flags, dig);
-    else
-        ZKM_LAUNCH((k_msm_digits<0, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
-                   (uint32_t*)nullptr, flags, dig);
+    {
+        // the histogram pass: all scalars at once, or chunk by chunk behind the caller's copies (ScalarFeed)
+        ScalarFeed whole;
+        whole.n = 1;
+        whole.begin[0] = 0;
+        whole.begin[1] = n;
+        const ScalarFeed& f = (feed && feed->n > 0) ? *feed : whole;
+        for (int ch = 0; ch < f.n; ch++) {
+            if (f.ev[ch]) ZKM_CUDA(cudaStreamWaitEvent(s, f.ev[ch], 0));
+            const uint64_t b = f.begin[ch], e = f.begin[ch + 1];
+            if (e <= b) continue;
+            const uint64_t need = (e - b + 255) / 256;
+            const unsigned grid = (unsigned)(need < grid_stream ? need : grid_stream);
+            if (wide)
+                ZKM_LAUNCH((k_msm_digits<0, 12>), grid, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
+                           (uint32_t*)nullptr, flags, dig, b, e);
+            else
+                ZKM_LAUNCH((k_msm_digits<0, 8>), grid, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1, counts,
+                           (uint32_t*)nullptr, flags, dig, b, e);
+        }
+    }
     exclusive_scan(c, counts, off, K + 1, s);
     ZKM_CUDA(cudaMemcpyAsync(cursor, off, K * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     if (one_scatter) {
         if (wide)
             ZKM_LAUNCH((k_msm_digits<1, 12>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1,
-                       cursor, idx, flags, (uint32_t*)nullptr);
+                       cursor, idx, flags, (uint32_t*)nullptr, (uint64_t)0, (uint64_t)n);
         else
             ZKM_LAUNCH((k_msm_digits<1, 8>), grid_stream, 256, 0, s, (const uint32_t*)d_scalars, d_inf, (uint64_t)n, pl, -1,
-                       cursor, idx, flags, (uint32_t*)nullptr);
+                       cursor, idx, flags, (uint32_t*)nullptr, (uint64_t)0, (uint64_t)n);
     } else {
         for (int w = 0; w < pl.W; w++)
             ZKM_LAUNCH(k_msm_scatter_row, grid_stream, 256, 0, s, (const uint32_t*)(dig + (size_t)w * n), (uint64_t)n, pl, w, cursor, idx);
@@ -538,42 +588,10 @@ void msm_run(Context* c, int curve, int group, const void* d_bases, const uint8_
     const void* cur_src = d_bases;
     const uint32_t* cur_idx = idx;
     {
-        int n_aff = c->opt.msm_affine_levels;
-        if (n_aff < 0) {
-            // Measured on B200 (profiles/experiment_affine_threshold_r1p.jsonl, BLS12-381 G1): a pairwise level costs
-            // ~0.33 ns per pair plus ~1 ms of fixed latency (inversion kernel, scans), the XYZZ accumulation it saves
-            // ~0.42 ns per entry -- so a level pays while it still has more than ~6 M pairs, and the whole scheme from
-            // ~24 M entries on (2^21 points: 18.9 -> 16.6 ms with two levels; 2^20: no gain).  Cheaper field products
-            // (BN254: 136 wide MADs instead of 300) raise both thresholds in proportion; they are NOT lowered for the
-            // heavier fields (G2, BW6-761), whose pair kernels run at 2 CTAs/SM and showed no gain below ~24 M entries
-            // (profiles/experiment_affine_rule_r1r.jsonl).
-            const double limbs = (double)ops->coord_bytes / 4.0 / (group == 2 && curve != ZKM_CURVE_BW6_761 ? 2.0 : 1.0);
-            const double mads = (2.0 * limbs * limbs + limbs) * (group == 2 && curve != ZKM_CURVE_BW6_761 ? 3.0 : 1.0);
-            const double scale = mads < 300.0 ? 300.0 / mads : 1.0;   // 1 for BLS12-381 G1
-            n_aff = 0;
-            if ((double)entries >= 24.0e6 * scale && entries < ((size_t)1 << 31)) {   // map words keep bit 31 for the pair flag
-                double avg = (double)entries / (double)K;   // a level needs lists of >= 4 entries on average
-                double pairs = (double)entries * 0.5;
-                while (n_aff < 8 && avg >= 4.0 && pairs > 6.0e6 * scale) {
-                    avg *= 0.5;
-                    pairs *= 0.5;
-                    n_aff++;
-                }
-            }
-        }
-        if (entries >= ((size_t)1 << 31)) n_aff = 0;   // (also when the level count was forced by option)
         const size_t CBy = ops->coord_bytes;
         const uint32_t m = (uint32_t)c->opt.msm_pair_m, m2 = (uint32_t)c->opt.msm_pair_m2;
         size_t Eb = entries;
         int p = 0;
-        // x coordinates of the bases in 64-byte slots for the level-0 forward gathers (one DRAM burst per x);
-        // rebuilt per call (2.5 GB of streaming traffic at 2^24, ~0.4 ms) -- not for tables of window multiples
-        const void* xarr = nullptr;
-        if (n_aff > 0 && ops->xarr_slot > 0 && !use_pre && c->opt.msm_xarr) {
-            void* xa = c->ws[WS_XARR].get(n * (size_t)ops->xarr_slot);
-            ops->build_xarr((unsigned)c->sm_count, s, d_bases, (uint64_t)n, xa);
-            xarr = xa;
-        }
         for (int lvl = 0; lvl < n_aff; lvl++) {
             const size_t Eout = (Eb + (K < Eb ? K : Eb)) / 2 + 1;      // bound on the outputs of this level
             const size_t nT = 32 * ((Eout + 32 * (size_t)m - 1) / (32 * (size_t)m)), nU = (nT + m2 - 1) / m2;   // chains (pair_chains)
