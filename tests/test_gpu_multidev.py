@@ -234,3 +234,38 @@ def test_profile_counters_are_exact(zkm2):
     want_xy, want_inf = capi.msm(0, 1, bases, scal)
     rec = d_out.cpu().numpy().view(np.uint64)
     assert np.array_equal(rec[:-1], want_xy)
+
+
+def test_sharded_host_msm_with_chunked_scalar_upload(zkm2):
+    """Shards of >= 2^22 scalars take the chunked upload of the host entry points (copy stream + one event per chunk, the
+    histogram pass behind the copies) on EVERY owning device: 2^23 points sharded two ways == the unsharded MSM == the
+    known-discrete-log identity."""
+    import torch
+    from oracle.py import exact
+    curve = BLS12_381
+    log_n = 23
+    n = 1 << log_n
+    a0, d = 0x1234567, 0x89ABCDE
+    W = curve.fq.limbs64
+    L = zkm2._lib.lib()
+    d_bases = torch.empty((n, 2 * W), dtype=torch.int64, device="cuda:0")
+    zkm2._lib.check(L.zkm_testgen_progression_device(curve.curve_id, 1, a0, d, n, ctypes.c_void_p(d_bases.data_ptr()),
+                                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    scal = capi.random_scalars(curve.curve_id, n, seed=0x5EED0000 + log_n)
+    reg_s = zkm2.RegisteredBases.from_device(curve.name, 1, d_bases.data_ptr(), n, shard=True)
+    reg_1 = zkm2.RegisteredBases.from_device(curve.name, 1, d_bases.data_ptr(), n)
+    try:
+        got = [reg_s.msm(scal), reg_s.msm(scal), reg_1.msm(scal)]
+    finally:
+        reg_s.release()
+        reg_1.release()
+        del d_bases
+        torch.cuda.empty_cache()
+    s_int = scal.astype(object)
+    s_vals = sum(s_int[:, j] << (64 * j) for j in range(curve.fr.limbs64))
+    k = int(np.sum(s_vals * (a0 + np.arange(n, dtype=object) * d)) % curve.fr.modulus)
+    G = exact.Group(curve, 1)
+    b, _ = exact.point_to_bytes(curve, 1, G.mul(G.gen, k))
+    for g in got:
+        assert not g.infinity and g.xy.tobytes() == b
